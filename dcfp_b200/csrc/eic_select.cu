@@ -1,0 +1,227 @@
+// K2 -- EIC score update, exact per-group k-th order statistic, strict-> masks with per-layer
+// min-keep top-k fallback (sm_100a).  Follows pruners/dcfp_pruner.py:15-20 (EIC), :43-66
+// (get_thresh) and :68-92 (gen_channel_mask) of the reference.
+//
+// The reference spends ~10 tiny launches per BN layer on the update (600-1100 launches per
+// step) and a CPU sort per group for the threshold.  Here: ONE launch updates the concatenated
+// score vector of all layers, ONE launch (a CTA per group) radix-selects the exact thresholds,
+// ONE launch (a CTA per layer) writes the masks.  The vectors are <= ~54k floats, so this is
+// launch-latency bound by construction -- reported in microseconds, not as a roofline fraction.
+#include "common.cuh"
+
+namespace dcfp {
+namespace {
+
+// ---- K2a -------------------------------------------------------------------------------------
+// Bit-exact restatement of dcfp_pruner.py:18-20 in fp32:
+//   flag = grad*gamma > 0
+//   g    = flag*|grad| + (!flag)*eic            (bool * float products, then one add)
+//   eic  = eic*r + g*(1-r)                      (two rounded products, then one rounded add)
+// __fmul_rn/__fadd_rn forbid FMA contraction so the roundings match the reference's.
+__device__ __forceinline__ float eic_step(float grad, float gamma, float prev, float r, float omr) {
+  const bool flag = __fmul_rn(grad, gamma) > 0.f;
+  const float t1 = __fmul_rn(flag ? 1.f : 0.f, fabsf(grad));
+  const float t2 = __fmul_rn(flag ? 0.f : 1.f, prev);
+  const float g = __fadd_rn(t1, t2);
+  return __fadd_rn(__fmul_rn(prev, r), __fmul_rn(g, omr));
+}
+
+__global__ void eic_update_ptrs_kernel(const float* const* __restrict__ grad_ptrs, const float* const* __restrict__ gamma_ptrs,
+                                       const int32_t* __restrict__ offsets, float* __restrict__ eic, float r, float omr,
+                                       int first_step) {
+  const int l = blockIdx.x;
+  const int beg = offsets[l], n = offsets[l + 1] - beg;
+  const float* __restrict__ g = grad_ptrs[l];
+  const float* __restrict__ w = gamma_ptrs[l];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float prev = first_step ? 0.f : eic[beg + i];
+    eic[beg + i] = eic_step(g[i], w[i], prev, r, omr);
+  }
+}
+
+__global__ void eic_update_flat_kernel(const float* __restrict__ grad, const float* __restrict__ gamma, float* __restrict__ eic,
+                                       int n, float r, float omr, int first_step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) eic[i] = eic_step(grad[i], gamma[i], first_step ? 0.f : eic[i], r, omr);
+}
+
+// dgamma[c] = sum_k S1[k][c]  (fp64 sum over classes, rounded once to fp32)
+__global__ void reduce_classes_kernel(const double* __restrict__ S1, int K, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) s += S1[static_cast<size_t>(k) * C + c];
+  out[c] = static_cast<float>(s);
+}
+
+// ---- K2b -------------------------------------------------------------------------------------
+// order-preserving float -> uint key (ascending); +NaN sorts last like torch.sort
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int kSelThreads = 1024;
+
+// Block-wide exact k-th smallest key (0-based) among the elements enumerated by `visit`.
+// visit(f) calls f(key) for every element owned by this thread.  4 MSB-first 8-bit passes.
+template <typename Visit>
+__device__ uint32_t block_radix_select(Visit visit, long long k, uint32_t* hist /*[256]*/, uint32_t* bcast /*[2]*/) {
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    visit([&](uint32_t key) {
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long rem = k;
+      int d = 0;
+      for (; d < 255; ++d) {
+        if (rem < static_cast<long long>(hist[d])) break;
+        rem -= hist[d];
+      }
+      bcast[0] = static_cast<uint32_t>(d);
+      bcast[1] = static_cast<uint32_t>(rem);
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    mask |= 0xffu << shift;
+    k = bcast[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// one CTA per group: thresh[g] = k_idx[g]-th smallest score among the layers of group g
+__global__ void __launch_bounds__(kSelThreads) group_thresh_kernel(const float* __restrict__ score,
+                                                                   const int32_t* __restrict__ layer_off,
+                                                                   const int32_t* __restrict__ layer_group, int n_layers,
+                                                                   long long k0, long long k1, float* __restrict__ thresh_out) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bcast[2];
+  const int g = blockIdx.x;
+  const long long k = g == 0 ? k0 : k1;
+  if (k < 0) {  // empty group: the reference leaves thresh[g] = 0 (dcfp_pruner.py:58-60)
+    if (threadIdx.x == 0) thresh_out[g] = 0.f;
+    return;
+  }
+  auto visit = [&](auto&& f) {
+    for (int l = 0; l < n_layers; ++l) {
+      if (layer_group[l] != g) continue;
+      const int end = layer_off[l + 1];
+      for (int i = layer_off[l] + threadIdx.x; i < end; i += blockDim.x) f(f2key(score[i]));
+    }
+  };
+  const uint32_t key = block_radix_select(visit, k, hist, bcast);
+  if (threadIdx.x == 0) thresh_out[g] = key2f(key);
+}
+
+constexpr int kMaskThreads = 256;
+
+// one CTA per layer: mask = score > thresh[group]; min-keep fallback (dcfp_pruner.py:77-82)
+__global__ void __launch_bounds__(kMaskThreads) layer_mask_kernel(const float* __restrict__ score,
+                                                                  const int32_t* __restrict__ layer_off,
+                                                                  const int32_t* __restrict__ layer_group,
+                                                                  const int32_t* __restrict__ min_keep,
+                                                                  const float* __restrict__ thresh, float* __restrict__ mask_out,
+                                                                  int32_t* __restrict__ kept_out) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bcast[2];
+  __shared__ int s_count;
+  const int l = blockIdx.x;
+  const int beg = layer_off[l], C = layer_off[l + 1] - beg;
+  const float t = thresh[layer_group[l]];
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const bool keep = score[beg + i] > t;
+    mask_out[beg + i] = keep ? 1.f : 0.f;
+    local += keep;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_count, local);
+  __syncthreads();
+  int kept = s_count;
+  const int mk = min(min_keep[l], C);
+  if (kept < mk) {
+    // keep the mk highest scores: everything above the mk-th largest value, then fill with the
+    // lowest-index elements equal to it (torch.sort's tie order is implementation-defined)
+    auto visit = [&](auto&& f) {
+      for (int i = threadIdx.x; i < C; i += blockDim.x) f(f2key(score[beg + i]));
+    };
+    const uint32_t kth = block_radix_select(visit, static_cast<long long>(C - mk), hist, bcast);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int above = 0;
+      for (int i = 0; i < C; ++i) above += f2key(score[beg + i]) > kth;
+      int need = mk - above;
+      for (int i = 0; i < C; ++i) {
+        const uint32_t key = f2key(score[beg + i]);
+        if (key > kth) mask_out[beg + i] = 1.f;
+        else if (key == kth && need > 0) {
+          mask_out[beg + i] = 1.f;
+          --need;
+        }
+      }
+      int total = 0;
+      for (int i = 0; i < C; ++i) total += mask_out[beg + i] != 0.f;
+      s_count = total;
+    }
+    __syncthreads();
+    kept = s_count;
+  }
+  if (threadIdx.x == 0 && kept_out) kept_out[l] = kept;
+}
+
+}  // namespace
+}  // namespace dcfp
+
+using namespace dcfp;
+
+extern "C" int dcfp_eic_update(const float* const* grad_ptrs, const float* const* gamma_ptrs, const int32_t* offsets,
+                               int n_layers, float* eic, float r, float one_minus_r, int first_step, void* stream) {
+  DCFP_REQUIRE(grad_ptrs && gamma_ptrs && offsets && eic, DCFP_EINVAL, "eic_update: null pointer");
+  DCFP_REQUIRE(n_layers > 0, DCFP_EINVAL, "eic_update: n_layers=%d", n_layers);
+  eic_update_ptrs_kernel<<<n_layers, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_ptrs, gamma_ptrs, offsets, eic, r,
+                                                                                  one_minus_r, first_step);
+  return finish_launch("eic_update");
+}
+
+extern "C" int dcfp_eic_update_flat(const float* grad, const float* gamma, float* eic, int n, float r, float one_minus_r,
+                                    int first_step, void* stream) {
+  DCFP_REQUIRE(grad && gamma && eic, DCFP_EINVAL, "eic_update_flat: null pointer");
+  DCFP_REQUIRE(n > 0, DCFP_EINVAL, "eic_update_flat: n=%d", n);
+  eic_update_flat_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad, gamma, eic, n, r, one_minus_r,
+                                                                                         first_step);
+  return finish_launch("eic_update_flat");
+}
+
+extern "C" int dcfp_reduce_classes(const double* S1, int K, int C, float* out, void* stream) {
+  DCFP_REQUIRE(S1 && out, DCFP_EINVAL, "reduce_classes: null pointer");
+  DCFP_REQUIRE(K > 0 && C > 0, DCFP_EINVAL, "reduce_classes: K=%d C=%d", K, C);
+  reduce_classes_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(S1, K, C, out);
+  return finish_launch("reduce_classes");
+}
+
+extern "C" int dcfp_thresh_mask(const float* score, const int32_t* layer_off, const int32_t* layer_group, const int32_t* min_keep,
+                                int n_layers, int n_total, const int64_t* k_idx_host, float* mask_out, float* thresh_out,
+                                int32_t* kept_out, void* stream) {
+  DCFP_REQUIRE(score && layer_off && layer_group && min_keep && k_idx_host && mask_out && thresh_out, DCFP_EINVAL,
+               "thresh_mask: null pointer");
+  DCFP_REQUIRE(n_layers > 0 && n_total > 0, DCFP_EINVAL, "thresh_mask: n_layers=%d n_total=%d", n_layers, n_total);
+  DCFP_REQUIRE(k_idx_host[0] < n_total && k_idx_host[1] < n_total, DCFP_EINVAL,
+               "thresh_mask: threshold index out of range (global_percent >= 1?)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  group_thresh_kernel<<<2, kSelThreads, 0, s>>>(score, layer_off, layer_group, n_layers, k_idx_host[0], k_idx_host[1],
+                                                thresh_out);
+  int rc = finish_launch("group_thresh");
+  if (rc) return rc;
+  layer_mask_kernel<<<n_layers, kMaskThreads, 0, s>>>(score, layer_off, layer_group, min_keep, thresh_out, mask_out, kept_out);
+  return finish_launch("layer_mask");
+}

@@ -1,0 +1,326 @@
+// torch.ops.dcfp.* -- the thin PyTorch registration over the C ABI of include/dcfp_b200.h.
+//
+// Everything here is plumbing: validate device / dtype / contiguity, unwrap tensors to raw device
+// pointers, fetch the CURRENT CUDA stream, call the extern "C" entry point, turn a non-zero return
+// code into a RuntimeError carrying dcfp_last_error().  No arithmetic lives in this file and there
+// is no CPU implementation registered: calling an op with CPU tensors raises.
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include <vector>
+
+#include "dcfp_b200.h"
+
+namespace {
+
+using at::Tensor;
+using c10::optional;
+
+void check_rc(int rc, const char* op) {
+  TORCH_CHECK(rc == 0, "dcfp::", op, " failed (", rc, "): ", dcfp_last_error());
+}
+
+void* cur_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().stream()); }
+
+void require_cuda(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), "dcfp: `", name, "` must be a CUDA tensor (there is no CPU fallback)");
+}
+
+int label_dtype_of(const Tensor& label) {
+  switch (label.scalar_type()) {
+    case at::kByte: return DCFP_LABEL_U8;
+    case at::kInt: return DCFP_LABEL_I32;
+    case at::kLong: return DCFP_LABEL_I64;
+    default: TORCH_CHECK(false, "dcfp: label dtype must be uint8 / int32 / int64, got ", label.scalar_type());
+  }
+}
+
+// Fills one descriptor; keeps nothing alive (the caller holds the tensors).
+dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const optional<Tensor>& scale,
+                          const optional<Tensor>& shift, const optional<Tensor>& label, const Tensor& S1, const Tensor& S2,
+                          const optional<Tensor>& cnt, int64_t K) {
+  require_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 4, "dcfp: feature map must be 4-D [N,C,h,w], got ", x.dim(), "-D");
+  TORCH_CHECK(x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16, "dcfp: feature map must be fp32 or bf16");
+  dcfp_layer_desc d{};
+  const bool nchw = x.is_contiguous();
+  const bool nhwc = !nchw && x.is_contiguous(at::MemoryFormat::ChannelsLast);
+  TORCH_CHECK(nchw || nhwc, "dcfp: feature map must be contiguous (NCHW) or channels_last");
+  d.layout = nchw ? DCFP_NCHW : DCFP_NHWC;
+  d.dtype = x.scalar_type() == at::kFloat ? DCFP_F32 : DCFP_BF16;
+  d.x = x.data_ptr();
+  d.N = static_cast<int32_t>(x.size(0));
+  d.C = static_cast<int32_t>(x.size(1));
+  d.h = static_cast<int32_t>(x.size(2));
+  d.w = static_cast<int32_t>(x.size(3));
+  d.K = static_cast<int32_t>(K);
+  if (dy.has_value()) {
+    const Tensor& g = *dy;
+    require_cuda(g, "dy");
+    TORCH_CHECK(g.sizes() == x.sizes() && g.scalar_type() == x.scalar_type(), "dcfp: dy must match x in shape and dtype");
+    TORCH_CHECK(nchw ? g.is_contiguous() : g.is_contiguous(at::MemoryFormat::ChannelsLast), "dcfp: dy must share x's layout");
+    d.dy = g.data_ptr();
+  }
+  auto per_channel = [&](const optional<Tensor>& t, const char* name) -> const float* {
+    if (!t.has_value()) return nullptr;
+    require_cuda(*t, name);
+    TORCH_CHECK(t->scalar_type() == at::kFloat && t->is_contiguous() && t->numel() == x.size(1), "dcfp: `", name,
+                "` must be a contiguous fp32 [C] tensor");
+    return t->data_ptr<float>();
+  };
+  d.scale = per_channel(scale, "scale");
+  d.shift = per_channel(shift, "shift");
+  if (label.has_value()) {
+    const Tensor& l = *label;
+    require_cuda(l, "label");
+    TORCH_CHECK(l.dim() == 3 && l.size(0) == x.size(0) && l.is_contiguous(), "dcfp: label must be contiguous [N,H0,W0]");
+    d.label = l.data_ptr();
+    d.label_dtype = label_dtype_of(l);
+    d.H0 = static_cast<int32_t>(l.size(1));
+    d.W0 = static_cast<int32_t>(l.size(2));
+  }
+  auto arena = [&](const Tensor& t, const char* name, int64_t numel) -> double* {
+    require_cuda(t, name);
+    TORCH_CHECK(t.scalar_type() == at::kDouble && t.is_contiguous() && t.numel() == numel, "dcfp: `", name,
+                "` must be a contiguous fp64 tensor of ", numel, " elements");
+    return t.data_ptr<double>();
+  };
+  d.S1 = arena(S1, "S1", K * x.size(1));
+  d.S2 = arena(S2, "S2", K * x.size(1));
+  if (cnt.has_value()) d.cnt = arena(*cnt, "cnt", K);
+  return d;
+}
+
+void class_stats(const Tensor& x, const optional<Tensor>& dy, const optional<Tensor>& scale, const optional<Tensor>& shift,
+                 const optional<Tensor>& label, Tensor S1, Tensor S2, optional<Tensor> cnt, int64_t K) {
+  const dcfp_layer_desc d = make_desc(x, dy, scale, shift, label, S1, S2, cnt, K);
+  c10::cuda::CUDAGuard guard(x.device());
+  check_rc(dcfp_class_stats(&d, cur_stream()), "class_stats");
+}
+
+void class_stats_grouped(at::TensorList xs, at::TensorList dys, at::TensorList scales, at::TensorList shifts,
+                         const optional<Tensor>& label, at::TensorList S1s, at::TensorList S2s, at::TensorList cnts,
+                         int64_t K) {
+  const size_t n = xs.size();
+  TORCH_CHECK(n > 0, "dcfp::class_stats_grouped: empty layer list");
+  TORCH_CHECK(S1s.size() == n && S2s.size() == n, "dcfp::class_stats_grouped: S1/S2 lists must match xs");
+  TORCH_CHECK(dys.empty() || dys.size() == n, "dcfp::class_stats_grouped: dys must be empty or match xs");
+  TORCH_CHECK(scales.size() == shifts.size() && (scales.empty() || scales.size() == n),
+              "dcfp::class_stats_grouped: scales/shifts must be empty or match xs");
+  TORCH_CHECK(cnts.empty() || cnts.size() == n, "dcfp::class_stats_grouped: cnts must be empty or match xs");
+  std::vector<dcfp_layer_desc> descs(n);
+  for (size_t i = 0; i < n; ++i) {
+    optional<Tensor> dy = dys.empty() ? optional<Tensor>() : optional<Tensor>(dys[i]);
+    optional<Tensor> sc = scales.empty() ? optional<Tensor>() : optional<Tensor>(scales[i]);
+    optional<Tensor> sf = shifts.empty() ? optional<Tensor>() : optional<Tensor>(shifts[i]);
+    // an empty tensor in `cnts` means "do not count for this layer"
+    optional<Tensor> ct = (cnts.empty() || cnts[i].numel() == 0) ? optional<Tensor>() : optional<Tensor>(cnts[i]);
+    descs[i] = make_desc(xs[i], dy, sc, sf, label, S1s[i], S2s[i], ct, K);
+  }
+  c10::cuda::CUDAGuard guard(xs[0].device());
+  for (size_t first = 0; first < n; first += DCFP_MAX_GROUP_LAYERS) {
+    const int m = static_cast<int>(std::min<size_t>(DCFP_MAX_GROUP_LAYERS, n - first));
+    check_rc(dcfp_class_stats_grouped(descs.data() + first, m, cur_stream()), "class_stats_grouped");
+  }
+}
+
+Tensor reduce_classes(const Tensor& S1) {
+  require_cuda(S1, "S1");
+  TORCH_CHECK(S1.dim() == 2 && S1.scalar_type() == at::kDouble && S1.is_contiguous(), "dcfp::reduce_classes: S1 must be fp64 [K,C]");
+  Tensor out = at::empty({S1.size(1)}, S1.options().dtype(at::kFloat));
+  c10::cuda::CUDAGuard guard(S1.device());
+  check_rc(dcfp_reduce_classes(S1.data_ptr<double>(), static_cast<int>(S1.size(0)), static_cast<int>(S1.size(1)),
+                               out.data_ptr<float>(), cur_stream()),
+           "reduce_classes");
+  return out;
+}
+
+// pointer table for the one-launch EIC update: built on the host, shipped with one async copy
+void eic_update(at::TensorList grads, at::TensorList gammas, const Tensor& offsets, Tensor eic, double r, double one_minus_r,
+                bool first_step) {
+  const size_t n = grads.size();
+  TORCH_CHECK(n > 0 && gammas.size() == n, "dcfp::eic_update: grads/gammas must be equally long, non-empty lists");
+  require_cuda(eic, "eic");
+  TORCH_CHECK(eic.scalar_type() == at::kFloat && eic.is_contiguous(), "dcfp::eic_update: eic must be contiguous fp32");
+  require_cuda(offsets, "offsets");
+  TORCH_CHECK(offsets.scalar_type() == at::kInt && offsets.is_contiguous() && offsets.numel() == static_cast<int64_t>(n) + 1,
+              "dcfp::eic_update: offsets must be int32 [n_layers+1]");
+  Tensor table = at::empty({static_cast<int64_t>(2 * n)}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
+  int64_t* t = table.data_ptr<int64_t>();
+  for (size_t i = 0; i < n; ++i) {
+    require_cuda(grads[i], "grad");
+    require_cuda(gammas[i], "gamma");
+    TORCH_CHECK(grads[i].scalar_type() == at::kFloat && gammas[i].scalar_type() == at::kFloat && grads[i].is_contiguous() &&
+                    gammas[i].is_contiguous() && grads[i].numel() == gammas[i].numel(),
+                "dcfp::eic_update: layer ", i, ": grad/gamma must be contiguous fp32 of equal length");
+    t[i] = reinterpret_cast<int64_t>(grads[i].data_ptr<float>());
+    t[n + i] = reinterpret_cast<int64_t>(gammas[i].data_ptr<float>());
+  }
+  c10::cuda::CUDAGuard guard(eic.device());
+  Tensor dev = table.to(eic.device(), /*non_blocking=*/true);
+  const float* const* gp = reinterpret_cast<const float* const*>(dev.data_ptr<int64_t>());
+  check_rc(dcfp_eic_update(gp, gp + n, offsets.data_ptr<int32_t>(), static_cast<int>(n), eic.data_ptr<float>(),
+                           static_cast<float>(r), static_cast<float>(one_minus_r), first_step ? 1 : 0, cur_stream()),
+           "eic_update");
+}
+
+void eic_update_flat(const Tensor& grad, const Tensor& gamma, Tensor eic, double r, double one_minus_r, bool first_step) {
+  require_cuda(grad, "grad");
+  require_cuda(gamma, "gamma");
+  require_cuda(eic, "eic");
+  TORCH_CHECK(grad.scalar_type() == at::kFloat && gamma.scalar_type() == at::kFloat && eic.scalar_type() == at::kFloat,
+              "dcfp::eic_update_flat: fp32 tensors required");
+  TORCH_CHECK(grad.is_contiguous() && gamma.is_contiguous() && eic.is_contiguous() && grad.numel() == eic.numel() &&
+                  gamma.numel() == eic.numel(),
+              "dcfp::eic_update_flat: contiguous tensors of equal length required");
+  c10::cuda::CUDAGuard guard(eic.device());
+  check_rc(dcfp_eic_update_flat(grad.data_ptr<float>(), gamma.data_ptr<float>(), eic.data_ptr<float>(),
+                                static_cast<int>(eic.numel()), static_cast<float>(r), static_cast<float>(one_minus_r),
+                                first_step ? 1 : 0, cur_stream()),
+           "eic_update_flat");
+}
+
+std::tuple<Tensor, Tensor, Tensor> thresh_mask(const Tensor& score, const Tensor& layer_off, const Tensor& layer_group,
+                                               const Tensor& min_keep, int64_t k0, int64_t k1) {
+  require_cuda(score, "score");
+  require_cuda(layer_off, "layer_off");
+  require_cuda(layer_group, "layer_group");
+  require_cuda(min_keep, "min_keep");
+  TORCH_CHECK(score.scalar_type() == at::kFloat && score.is_contiguous() && score.dim() == 1, "dcfp::thresh_mask: score must be fp32 [n]");
+  const int64_t n_layers = layer_group.numel();
+  TORCH_CHECK(layer_off.scalar_type() == at::kInt && layer_group.scalar_type() == at::kInt && min_keep.scalar_type() == at::kInt,
+              "dcfp::thresh_mask: layer tables must be int32");
+  TORCH_CHECK(layer_off.numel() == n_layers + 1 && min_keep.numel() == n_layers, "dcfp::thresh_mask: layer table sizes disagree");
+  Tensor mask = at::empty_like(score);
+  Tensor thresh = at::empty({2}, score.options());
+  Tensor kept = at::empty({n_layers}, layer_off.options());
+  const int64_t k_idx[2] = {k0, k1};
+  c10::cuda::CUDAGuard guard(score.device());
+  check_rc(dcfp_thresh_mask(score.data_ptr<float>(), layer_off.data_ptr<int32_t>(), layer_group.data_ptr<int32_t>(),
+                            min_keep.data_ptr<int32_t>(), static_cast<int>(n_layers), static_cast<int>(score.numel()), k_idx,
+                            mask.data_ptr<float>(), thresh.data_ptr<float>(), kept.data_ptr<int32_t>(), cur_stream()),
+           "thresh_mask");
+  return {mask, thresh, kept};
+}
+
+struct GatherShape {
+  int64_t O, I, khw;
+};
+GatherShape gather_shape(const Tensor& src) {
+  TORCH_CHECK(src.dim() >= 1, "dcfp::channel_gather: scalar tensor");
+  GatherShape g{src.size(0), src.dim() >= 2 ? src.size(1) : 1, 1};
+  for (int64_t d = 2; d < src.dim(); ++d) g.khw *= src.size(d);
+  return g;
+}
+const int32_t* idx_ptr(const optional<Tensor>& idx, const char* name) {
+  if (!idx.has_value()) return nullptr;
+  require_cuda(*idx, name);
+  TORCH_CHECK(idx->scalar_type() == at::kInt && idx->is_contiguous() && idx->dim() == 1, "dcfp::channel_gather: `", name,
+              "` must be int32 [n]");
+  return idx->data_ptr<int32_t>();
+}
+std::vector<int64_t> gathered_sizes(const Tensor& src, const optional<Tensor>& out_idx, const optional<Tensor>& in_idx) {
+  std::vector<int64_t> sizes = src.sizes().vec();
+  if (out_idx.has_value()) sizes[0] = out_idx->numel();
+  if (in_idx.has_value()) {
+    TORCH_CHECK(src.dim() >= 2, "dcfp::channel_gather: in_idx given for a 1-D tensor");
+    sizes[1] = in_idx->numel();
+  }
+  return sizes;
+}
+
+Tensor channel_gather(const Tensor& src, const optional<Tensor>& out_idx, const optional<Tensor>& in_idx) {
+  require_cuda(src, "src");
+  TORCH_CHECK(src.is_contiguous(), "dcfp::channel_gather: src must be contiguous");
+  const int es = static_cast<int>(src.element_size());
+  const GatherShape g = gather_shape(src);
+  Tensor dst = at::empty(gathered_sizes(src, out_idx, in_idx), src.options());
+  const int n_out = static_cast<int>(dst.size(0));
+  const int n_in = src.dim() >= 2 ? static_cast<int>(dst.size(1)) : 1;
+  c10::cuda::CUDAGuard guard(src.device());
+  check_rc(dcfp_channel_gather(src.data_ptr(), dst.data_ptr(), idx_ptr(out_idx, "out_idx"), n_out, idx_ptr(in_idx, "in_idx"), n_in,
+                               static_cast<int>(g.I), static_cast<int>(g.khw), es, cur_stream()),
+           "channel_gather");
+  return dst;
+}
+
+// an index tensor with numel()==0 and dim()==0 ... cannot express "keep all"; use a parallel bool list instead
+std::vector<Tensor> channel_gather_grouped(at::TensorList srcs, at::TensorList out_idx, at::TensorList in_idx,
+                                           at::IntArrayRef has_out, at::IntArrayRef has_in) {
+  const size_t n = srcs.size();
+  TORCH_CHECK(n > 0 && out_idx.size() == n && in_idx.size() == n && has_out.size() == n && has_in.size() == n,
+              "dcfp::channel_gather_grouped: list lengths disagree");
+  std::vector<Tensor> dsts(n);
+  std::vector<dcfp_gather_desc> descs(n);
+  const int es = static_cast<int>(srcs[0].element_size());
+  for (size_t i = 0; i < n; ++i) {
+    const Tensor& src = srcs[i];
+    require_cuda(src, "src");
+    TORCH_CHECK(src.is_contiguous() && static_cast<int>(src.element_size()) == es,
+                "dcfp::channel_gather_grouped: sources must be contiguous and share one element size");
+    optional<Tensor> oi = has_out[i] ? optional<Tensor>(out_idx[i]) : optional<Tensor>();
+    optional<Tensor> ii = has_in[i] ? optional<Tensor>(in_idx[i]) : optional<Tensor>();
+    const GatherShape g = gather_shape(src);
+    dsts[i] = at::empty(gathered_sizes(src, oi, ii), src.options());
+    descs[i] = dcfp_gather_desc{src.data_ptr(),
+                                dsts[i].data_ptr(),
+                                idx_ptr(oi, "out_idx"),
+                                idx_ptr(ii, "in_idx"),
+                                static_cast<int32_t>(dsts[i].size(0)),
+                                static_cast<int32_t>(src.dim() >= 2 ? dsts[i].size(1) : 1),
+                                static_cast<int32_t>(g.I),
+                                static_cast<int32_t>(g.khw)};
+  }
+  c10::cuda::CUDAGuard guard(srcs[0].device());
+  const size_t ws_bytes = dcfp_channel_gather_workspace(static_cast<int>(n));
+  Tensor ws = at::empty({static_cast<int64_t>((ws_bytes + 7) / 8)}, srcs[0].options().dtype(at::kLong));
+  check_rc(dcfp_channel_gather_grouped(descs.data(), static_cast<int>(n), es, ws.data_ptr(), ws_bytes, cur_stream()),
+           "channel_gather_grouped");
+  return dsts;
+}
+
+Tensor bias_comp(const Tensor& W, const Tensor& act) {
+  require_cuda(W, "W");
+  require_cuda(act, "act");
+  TORCH_CHECK(W.scalar_type() == at::kFloat && W.is_contiguous() && W.dim() >= 2, "dcfp::bias_comp: W must be contiguous fp32 [O,I,...]");
+  TORCH_CHECK(act.scalar_type() == at::kFloat && act.is_contiguous() && act.numel() == W.size(1),
+              "dcfp::bias_comp: act must be contiguous fp32 [I]");
+  const GatherShape g = gather_shape(W);
+  Tensor out = at::empty({W.size(0)}, W.options());
+  c10::cuda::CUDAGuard guard(W.device());
+  check_rc(dcfp_bias_comp(W.data_ptr<float>(), static_cast<int>(g.O), static_cast<int>(g.I), static_cast<int>(g.khw),
+                          act.data_ptr<float>(), out.data_ptr<float>(), cur_stream()),
+           "bias_comp");
+  return out;
+}
+
+int64_t launch_count(bool reset) { return dcfp_launch_count(reset ? 1 : 0); }
+int64_t abi_version() { return dcfp_abi_version(); }
+
+}  // namespace
+
+TORCH_LIBRARY(dcfp, m) {
+  m.def(
+      "class_stats(Tensor x, Tensor? dy, Tensor? scale, Tensor? shift, Tensor? label, Tensor(a!) S1, Tensor(b!) S2, "
+      "Tensor(c!)? cnt, int K) -> ()",
+      &class_stats);
+  m.def(
+      "class_stats_grouped(Tensor[] xs, Tensor[] dys, Tensor[] scales, Tensor[] shifts, Tensor? label, Tensor(a!)[] S1s, "
+      "Tensor(b!)[] S2s, Tensor(c!)[] cnts, int K) -> ()",
+      &class_stats_grouped);
+  m.def("reduce_classes(Tensor S1) -> Tensor", &reduce_classes);
+  m.def("eic_update(Tensor[] grads, Tensor[] gammas, Tensor offsets, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",
+        &eic_update);
+  m.def("eic_update_flat(Tensor grad, Tensor gamma, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",
+        &eic_update_flat);
+  m.def("thresh_mask(Tensor score, Tensor layer_off, Tensor layer_group, Tensor min_keep, int k0, int k1) -> (Tensor, Tensor, Tensor)",
+        &thresh_mask);
+  m.def("channel_gather(Tensor src, Tensor? out_idx, Tensor? in_idx) -> Tensor", &channel_gather);
+  m.def("channel_gather_grouped(Tensor[] srcs, Tensor[] out_idx, Tensor[] in_idx, int[] has_out, int[] has_in) -> Tensor[]",
+        &channel_gather_grouped);
+  m.def("bias_comp(Tensor W, Tensor act) -> Tensor", &bias_comp);
+  m.def("launch_count(bool reset) -> int", &launch_count);
+  m.def("abi_version() -> int", &abi_version);
+}

@@ -1,0 +1,97 @@
+"""Loader and thin wrappers for torch.ops.dcfp.* (the C ABI registered as PyTorch ops).
+
+There is NO fallback: if the native library is missing, or a tensor lives on the CPU, the call
+raises.  `require_gpu()` is what product entry points call first.
+"""
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OPS_LIB = os.path.join(HERE, "lib", "dcfp_torch_ops.so")
+
+_loaded = False
+
+
+def load():
+    """Registers torch.ops.dcfp.* (idempotent)."""
+    global _loaded
+    if _loaded:
+        return torch.ops.dcfp
+    if not os.path.exists(OPS_LIB):
+        raise RuntimeError("dcfp_b200 native library not built: %s is missing. Run `python -m dcfp_b200.build` "
+                           "(nvcc, sm_100a). There is no CPU or eager fallback." % OPS_LIB)
+    torch.ops.load_library(OPS_LIB)
+    _loaded = True
+    return torch.ops.dcfp
+
+
+def require_gpu():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dcfp_b200 needs a CUDA device (B200 / sm_100a): the scoring, mask and gather kernels "
+                           "have no CPU fallback.")
+    return load()
+
+
+def launch_count(reset=False):
+    return int(load().launch_count(bool(reset)))
+
+
+# ---- K1 ----------------------------------------------------------------------------------------
+def class_stats(x, label, K, S1, S2, cnt=None, dy=None, scale=None, shift=None):
+    """S1[k,c] += sum v, S2[k,c] += sum v*v, cnt[k] += #px over pixels whose nearest-down-sampled label is k."""
+    load().class_stats(x, dy, scale, shift, label, S1, S2, cnt, int(K))
+
+
+def class_stats_grouped(xs, label, K, S1s, S2s, cnts=None, dys=None, scales=None, shifts=None):
+    """One launch over many resident feature maps (same dtype / K / functor)."""
+    load().class_stats_grouped(list(xs), list(dys or []), list(scales or []), list(shifts or []), label, list(S1s), list(S2s),
+                               list(cnts or []), int(K))
+
+
+def reduce_classes(S1):
+    return load().reduce_classes(S1)
+
+
+# ---- K2 ----------------------------------------------------------------------------------------
+def r_pair(r):
+    """(float32(r), float32(1 - r)) exactly as `eic*r + g*(1-r)` sees them (dcfp_pruner.py:20)."""
+    return float(torch.tensor(float(r), dtype=torch.float32)), float(torch.tensor(1.0 - float(r), dtype=torch.float32))
+
+
+def eic_update(grads, gammas, offsets, eic, r, first_step):
+    rr, omr = r_pair(r)
+    load().eic_update(list(grads), list(gammas), offsets, eic, rr, omr, bool(first_step))
+
+
+def eic_update_flat(grad, gamma, eic, r, first_step):
+    rr, omr = r_pair(r)
+    load().eic_update_flat(grad, gamma, eic, rr, omr, bool(first_step))
+
+
+def thresh_mask(score, layer_off, layer_group, min_keep, k0, k1):
+    """-> (mask fp32 [n], thresh fp32 [2], kept int32 [n_layers])"""
+    return load().thresh_mask(score, layer_off, layer_group, min_keep, int(k0), int(k1))
+
+
+# ---- K3 ----------------------------------------------------------------------------------------
+def channel_gather(src, out_idx=None, in_idx=None):
+    return load().channel_gather(src, out_idx, in_idx)
+
+
+def channel_gather_grouped(srcs, out_idx, in_idx):
+    """out_idx / in_idx: lists with None for "keep all"."""
+    dummy = None
+    oi, ii, ho, hi = [], [], [], []
+    for s, o, i in zip(srcs, out_idx, in_idx):
+        if dummy is None:
+            dummy = torch.empty(0, dtype=torch.int32, device=s.device)
+        oi.append(dummy if o is None else o)
+        ii.append(dummy if i is None else i)
+        ho.append(0 if o is None else 1)
+        hi.append(0 if i is None else 1)
+    return load().channel_gather_grouped(list(srcs), oi, ii, ho, hi)
+
+
+def bias_comp(W, act):
+    return load().bias_comp(W, act)

@@ -1,0 +1,148 @@
+/*
+ * dcfp_b200.h -- C ABI of the B200-native DCFP scoring -> keep-mask -> channel-gather path.
+ *
+ * This is the drop-in boundary.  The reference (wzx99/DCFP) is pure
+ * Python: its "FFI" for this path is the set of torch tensor ops issued by
+ * pruners/dcfp_pruner.py and pruners/channel_pruner.py.  Each entry point below names the
+ * reference lines it replaces.  The Python binding a maintainer adds on the reference side is
+ * shown in INTEGRATION.md (ctypes stub and the TORCH_LIBRARY binding in
+ * dcfp_b200/csrc/torch_binding.cpp).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - functions are re-entrant, hold no global state, never allocate device memory and never
+ *     synchronise the device or the stream (hooks call them from the autograd engine thread);
+ *   - return 0 on success, a negative DCFP_E* validation code, or a positive cudaError_t;
+ *     no C++ exception crosses the boundary; dcfp_last_error() returns a thread-local message.
+ */
+#ifndef DCFP_B200_H_
+#define DCFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCFP_ABI_VERSION 1
+
+/* element types of feature maps / weights */
+#define DCFP_F32 0
+#define DCFP_BF16 1
+/* label element types (reference: int64, train.py:253; datasets store uint8) */
+#define DCFP_LABEL_U8 0
+#define DCFP_LABEL_I32 1
+#define DCFP_LABEL_I64 2
+/* feature-map layouts */
+#define DCFP_NCHW 0
+#define DCFP_NHWC 1 /* torch.channels_last */
+
+#define DCFP_EINVAL (-1)      /* bad argument (null pointer, non-positive extent, unknown enum) */
+#define DCFP_EUNSUPPORTED (-2) /* valid but not implemented combination */
+#define DCFP_ETOOBIG (-3)     /* exceeds a documented limit (K > 255, too many layers, ...) */
+
+#define DCFP_MAX_CLASSES 255
+#define DCFP_MAX_GROUP_LAYERS 160
+
+/*
+ * One scored feature map (one BN layer of one micro-batch).
+ *
+ * value functor, per element of channel c at pixel p (n, i, j):
+ *   forward  (dy == NULL):  v = x * scale[c] + shift[c]            (scale/shift NULL -> 1 / 0)
+ *   backward (dy != NULL):  v = dy * (x * scale[c] + shift[c])     with scale = invstd,
+ *                           shift = -mean * invstd  => v = dy * xhat, and
+ *                           sum_k S1[k][c] == d(loss)/d(gamma_c)   (BN backward, the quantity
+ *                           pruners/dcfp_pruner.py:18 reads as m.weight.grad)
+ * class key:  k = label[n][min(floor(i * (float)H0 / h), H0-1)][min(floor(j * (float)W0 / w), W0-1)]
+ *             (legacy `nearest` of F.interpolate); k outside [0, K) -- e.g. the ignore label 255 --
+ *             is dropped.  label == NULL puts every pixel in class 0 (K must be 1).
+ * accumulates (+=, fp64):  S1[k*C + c] += sum v,  S2[k*C + c] += sum v*v,  cnt[k] += #pixels
+ *             (cnt may be NULL; pass it for ONE layer per label resolution).
+ */
+typedef struct dcfp_layer_desc {
+  const void* x;      /* [N,C,h,w] (NCHW) or [N,h,w,C] (NHWC), dtype `dtype` */
+  const void* dy;     /* same shape/dtype as x, or NULL */
+  const float* scale; /* [C] or NULL */
+  const float* shift; /* [C] or NULL */
+  const void* label;  /* [N,H0,W0] of label_dtype, or NULL */
+  double* S1;         /* [K,C] */
+  double* S2;         /* [K,C] */
+  double* cnt;        /* [K] or NULL */
+  int32_t N, C, h, w;
+  int32_t H0, W0;
+  int32_t K;
+  int32_t dtype;       /* DCFP_F32 | DCFP_BF16 */
+  int32_t layout;      /* DCFP_NCHW | DCFP_NHWC */
+  int32_t label_dtype; /* DCFP_LABEL_* */
+  int32_t reserved[2];
+} dcfp_layer_desc;
+
+/* ---- K1: label-keyed segmented reduction over conv/BN feature maps -------------------------
+ * north_star "class-conditional calibration statistics"; no reference counterpart for the
+ * forward functor; the backward functor restates the dgamma reduction of
+ * autograd's BN backward that feeds pruners/dcfp_pruner.py:18.                              */
+int dcfp_class_stats(const dcfp_layer_desc* desc_host, void* stream);
+/* Same, for up to DCFP_MAX_GROUP_LAYERS resident feature maps in ONE launch (all K, dtype,
+ * layout, dy-nullness must agree).  Layers only share the grid; outputs stay per layer.      */
+int dcfp_class_stats_grouped(const dcfp_layer_desc* descs_host, int n_layers, void* stream);
+
+/* ---- K2a: EIC update -- pruners/dcfp_pruner.py:15-20 ------------------------------------------
+ *   flag = grad*gamma > 0;  g = flag ? |grad| : eic;  eic = eic*r + g*(1-r)      (fp32, two
+ *   roundings then add, exactly the reference's association; first_step treats eic as 0).
+ * One launch over all layers: grad_ptrs/gamma_ptrs are device arrays of n_layers device
+ * pointers (fp32 [C_l]); offsets is a device array [n_layers+1] into the concatenated eic.   */
+int dcfp_eic_update(const float* const* grad_ptrs, const float* const* gamma_ptrs, const int32_t* offsets,
+                    int n_layers, float* eic, float r, float one_minus_r, int first_step, void* stream);
+/* Same on already-concatenated grad/gamma vectors of n floats. */
+int dcfp_eic_update_flat(const float* grad, const float* gamma, float* eic, int n, float r, float one_minus_r,
+                         int first_step, void* stream);
+/* dgamma[c] = sum_k S1[k*C + c]  (fp64 arena -> fp32), the bridge from K1-backward to K2a.     */
+int dcfp_reduce_classes(const double* S1, int K, int C, float* out, void* stream);
+
+/* ---- K2b: global threshold + keep masks -- pruners/dcfp_pruner.py:43-92 ------------------------
+ * score: concatenated fp32 scores of the n_layers scored layers; layer l owns
+ * [layer_off[l], layer_off[l+1]) and belongs to group layer_group[l] in {0,1}
+ * (get_bn_group, :36-37).  thresh[g] = k_idx[g]-th smallest score of group g (ascending, 0-based;
+ * get_thresh :59-64; k_idx[g] < 0 -> group empty, thresh 0).  mask = score > thresh (strict,
+ * :77); a layer with fewer than min_keep[l] survivors additionally keeps its min_keep[l]
+ * highest-scoring channels, ties broken lowest-index-first (:79-82; torch.sort's tie order is
+ * implementation-defined there).  All arrays are device arrays except k_idx_host[2].
+ * kept_out[l] (optional) receives the number of surviving channels of layer l.                 */
+int dcfp_thresh_mask(const float* score, const int32_t* layer_off, const int32_t* layer_group, const int32_t* min_keep,
+                     int n_layers, int n_total, const int64_t* k_idx_host, float* mask_out, float* thresh_out,
+                     int32_t* kept_out, void* stream);
+
+/* ---- K3: channel gather -- pruners/channel_pruner.py:907-948 (deploy_subnet) --------------------
+ * dst[o', i', :] = src[out_idx[o'], in_idx[i'], :] for a weight [O, I, khw] of elt_size-byte
+ * elements (khw = kh*kw, 1 for BN vectors/bias with I = 1).  in_idx NULL -> all I inputs kept. */
+int dcfp_channel_gather(const void* src, void* dst, const int32_t* out_idx, int n_out, const int32_t* in_idx, int n_in,
+                        int I, int khw, int elt_size, void* stream);
+typedef struct dcfp_gather_desc {
+  const void* src;
+  void* dst;
+  const int32_t* out_idx;
+  const int32_t* in_idx; /* or NULL */
+  int32_t n_out, n_in, I, khw;
+} dcfp_gather_desc;
+/* All weighted modules of a model in ONE launch.  desc_workspace: device scratch of at least
+ * dcfp_channel_gather_workspace(n) bytes; the table is copied there with cudaMemcpyAsync. */
+size_t dcfp_channel_gather_workspace(int n);
+int dcfp_channel_gather_grouped(const dcfp_gather_desc* descs_host, int n, int elt_size, void* desc_workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ---- bias compensation -- pruners/channel_pruner.py:873-905 (resize_subnet_bias) -----------------
+ * offset[o] = sum_i act[i] * sum_e W[o, i, e]   (fp32; act = relu((1 - in_mask) * beta_parent)) */
+int dcfp_bias_comp(const float* W, int O, int I, int khw, const float* act, float* offset_out, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------- */
+const char* dcfp_last_error(void);
+int dcfp_abi_version(void);
+/* number of kernels launched by this library in the calling thread since the last reset */
+int64_t dcfp_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCFP_B200_H_ */

@@ -1,0 +1,194 @@
+"""K1 parity: CUDA `class_stats` (through torch.ops.dcfp -> C ABI) vs the CPU oracle.
+
+Tolerance (fp32 accumulation inside a CTA, fp64 across CTAs):
+    |S - S_ref| <= RTOL * sum|v|  per (class, channel)     with RTOL = 1e-5
+counts are integers and must match exactly.
+"""
+import pytest
+import torch
+
+from oracle import class_stats_ref as ref
+
+RTOL = 1e-5
+pytestmark = pytest.mark.gpu
+
+
+def _labels(n, h0, w0, K, dtype, seed, blob=True):
+    g = torch.Generator().manual_seed(seed)
+    if blob:  # coarse random blocks -> coherent regions, then ~3% ignore
+        coarse = torch.randint(0, K, (n, max(h0 // 16, 1), max(w0 // 16, 1)), generator=g)
+        lab = torch.nn.functional.interpolate(coarse[:, None].float(), size=(h0, w0), mode="nearest")[:, 0].long()
+    else:
+        lab = torch.randint(0, K, (n, h0, w0), generator=g)
+    ign = torch.rand(n, h0, w0, generator=g) < 0.03
+    lab[ign] = 255
+    return lab.to(dtype)
+
+
+def _check(ops, x, label, K, dy=None, scale=None, shift=None, cnt=True):
+    dev = torch.device("cuda")
+    C = x.shape[1]
+    S1 = torch.zeros(K, C, dtype=torch.float64, device=dev)
+    S2 = torch.zeros_like(S1)
+    cn = torch.zeros(K, dtype=torch.float64, device=dev) if cnt else None
+    to = lambda t: None if t is None else t.to(dev)
+    xd = x.to(dev)
+    if x.dim() == 4 and not x.is_contiguous():
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    dyd = to(dy)
+    if dyd is not None and not x.is_contiguous():
+        dyd = dyd.contiguous(memory_format=torch.channels_last)
+    ops.class_stats(xd, to(label), K, S1, S2, cn, dy=dyd, scale=to(scale), shift=to(shift))
+    torch.cuda.synchronize()
+    v = ref.functor_fwd(x.float(), scale, shift) if dy is None else ref.functor_bwd(x.float(), dy.float(), scale, shift)
+    rc, r1, r2 = ref.class_stats(v, label, K)
+    mass = ref.abs_mass(v, label, K)
+    assert torch.equal(cn.cpu(), rc) if cnt else True
+    e1 = (S1.cpu() - r1).abs()
+    assert (e1 <= RTOL * mass + 1e-30).all(), "S1 max rel-to-mass err %.3g" % (e1 / (mass + 1e-30)).max()
+    e2 = (S2.cpu() - r2).abs()
+    assert (e2 <= RTOL * r2 + 1e-30).all(), "S2 max rel err %.3g" % (e2 / (r2 + 1e-30)).max()
+    return S1, S2, cn
+
+
+SHAPES = [
+    # N, C, h, w, H0, W0, K
+    (2, 256, 64, 128, 512, 1024, 19),   # the dominant c1/c2 shape
+    (2, 64, 128, 256, 512, 1024, 19),
+    (2, 48, 128, 128, 512, 512, 171),   # partial channel group, shared-atomic accumulators
+    (1, 33, 20, 36, 160, 288, 19),      # ragged: plane = 11 full segments + 16 px
+    (2, 512, 6, 6, 512, 512, 150),      # PSP pyramid stage (generic path)
+    (2, 256, 1, 1, 512, 1024, 19),      # ASPP image pooling (generic path)
+    (2, 64, 97, 97, 769, 769, 19),      # odd crop, non-integer label ratio (generic path)
+    (3, 96, 40, 52, 300, 411, 150),     # non-integer ratio on the tiled path
+    (2, 32, 64, 64, 64, 64, 2),         # label at feature resolution
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fwd_matches_oracle(native, shape, dtype):
+    from dcfp_b200 import ops
+    N, C, h, w, H0, W0, K = shape
+    g = torch.Generator().manual_seed(hash(shape) % 2**31)
+    x = (torch.randn(N, C, h, w, generator=g) * 1.5 + 0.3).to(dtype)
+    label = _labels(N, H0, W0, K, torch.uint8, seed=7 + C)
+    _check(ops, x, label, K)
+
+
+@pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int32, torch.int64])
+def test_label_dtypes_and_affine(native, label_dtype):
+    from dcfp_b200 import ops
+    N, C, h, w, K = 2, 128, 64, 64, 19
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, C, h, w, generator=g)
+    scale = torch.rand(C, generator=g) + 0.5
+    shift = torch.randn(C, generator=g)
+    label = _labels(N, 512, 512, K, label_dtype, seed=3)
+    _check(ops, x, label, K, scale=scale, shift=shift)
+
+
+def test_iid_labels_worst_case_runs(native):
+    from dcfp_b200 import ops
+    N, C, h, w, K = 2, 64, 64, 128, 19
+    x = torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(5))
+    label = _labels(N, h, w, K, torch.uint8, seed=9, blob=False)
+    _check(ops, x, label, K)
+
+
+def test_all_ignored_and_single_class(native):
+    from dcfp_b200 import ops
+    x = torch.randn(2, 64, 32, 64, generator=torch.Generator().manual_seed(1))
+    lab = torch.full((2, 256, 512), 255, dtype=torch.uint8)
+    S1, S2, cn = _check(ops, x, lab, 19)
+    assert S1.abs().sum() == 0 and cn.sum() == 0
+    _check(ops, x, torch.zeros(2, 256, 512, dtype=torch.uint8), 19)
+    # K == 1 without labels: plain per-channel sums
+    dev = torch.device("cuda")
+    S1 = torch.zeros(1, 64, dtype=torch.float64, device=dev)
+    S2 = torch.zeros_like(S1)
+    ops.class_stats(x.to(dev), None, 1, S1, S2)
+    assert torch.allclose(S1[0].cpu(), x.double().sum((0, 2, 3)), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bwd_functor(native, dtype):
+    from dcfp_b200 import ops
+    N, C, h, w, K = 2, 256, 64, 128, 19
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(N, C, h, w, generator=g) * 2 + 1).to(dtype)
+    dy = (torch.randn(N, C, h, w, generator=g) * 1e-3).to(dtype)
+    mean = x.float().mean((0, 2, 3))
+    invstd = 1.0 / torch.sqrt(x.float().var((0, 2, 3), unbiased=False) + 1e-5)
+    label = _labels(N, 512, 1024, K, torch.int64, seed=4)
+    _check(ops, x, label, K, dy=dy, scale=invstd, shift=-mean * invstd)
+
+
+def test_channels_last(native):
+    from dcfp_b200 import ops
+    N, C, h, w, K = 2, 96, 32, 64, 19
+    x = torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(2)).contiguous(memory_format=torch.channels_last)
+    label = _labels(N, 256, 512, K, torch.uint8, seed=8)
+    _check(ops, x, label, K)
+
+
+def test_grouped_equals_per_layer_and_accumulates(native):
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    K = 19
+    g = torch.Generator().manual_seed(33)
+    shapes = [(2, 64, 64, 128), (2, 256, 64, 128), (2, 128, 128, 256), (2, 256, 1, 1), (2, 48, 32, 64)]
+    xs = [torch.randn(*s, generator=g) for s in shapes]
+    label = _labels(2, 512, 1024, K, torch.uint8, seed=12)
+    xd = [x.to(dev) for x in xs]
+    ld = label.to(dev)
+    S1 = [torch.zeros(K, s[1], dtype=torch.float64, device=dev) for s in shapes]
+    S2 = [torch.zeros_like(t) for t in S1]
+    cnt = [torch.zeros(K, dtype=torch.float64, device=dev) for _ in shapes]
+    ops.class_stats_grouped(xd, ld, K, S1, S2, cnts=cnt)
+    ops.class_stats_grouped(xd, ld, K, S1, S2, cnts=cnt)  # += semantics: second pass doubles
+    torch.cuda.synchronize()
+    for x, a1, a2, c in zip(xs, S1, S2, cnt):
+        rc, r1, r2 = ref.class_stats(x, label, K)
+        mass = ref.abs_mass(x, label, K)
+        assert torch.equal(c.cpu(), 2 * rc)
+        assert ((a1.cpu() - 2 * r1).abs() <= 2 * RTOL * mass + 1e-30).all()
+        assert ((a2.cpu() - 2 * r2).abs() <= 2 * RTOL * r2 + 1e-30).all()
+
+
+def test_dgamma_equals_autograd(native):
+    """sum_k S1_bwd[k, c] must equal autograd's bn.weight.grad (the quantity dcfp_pruner.py:18 reads)."""
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    N, C, h, w, K = 2, 256, 64, 128, 19
+    bn = torch.nn.BatchNorm2d(C).to(dev).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    x = (torch.randn(N, C, h, w, device=dev) * 3 + 1).requires_grad_(True)
+    y = bn(x)
+    dy = torch.randn_like(y) * 1e-3
+    y.backward(dy)
+    mean = x.detach().mean((0, 2, 3))
+    invstd = 1.0 / torch.sqrt(x.detach().var((0, 2, 3), unbiased=False) + bn.eps)
+    label = _labels(N, 512, 1024, K, torch.int64, seed=6).to(dev)
+    label[label == 255] = 0  # dgamma sums over every pixel: no ignored ones here
+    S1 = torch.zeros(K, C, dtype=torch.float64, device=dev)
+    S2 = torch.zeros_like(S1)
+    ops.class_stats(x.detach(), label, K, S1, S2, dy=dy, scale=invstd, shift=-mean * invstd)
+    dgamma = ops.reduce_classes(S1)
+    ref_g = bn.weight.grad
+    tol = 1e-5 * ref_g.abs() + 1e-5 * ref_g.abs().mean()
+    assert ((dgamma - ref_g).abs() <= tol).all(), ((dgamma - ref_g).abs() / tol).max()
+
+
+def test_validation_errors(native):
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    x = torch.randn(1, 8, 4, 4, device=dev)
+    S = torch.zeros(300, 8, dtype=torch.float64, device=dev)
+    with pytest.raises(RuntimeError, match="K=300"):
+        ops.class_stats(x, torch.zeros(1, 4, 4, dtype=torch.uint8, device=dev), 300, S, S.clone())
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.class_stats(x.cpu(), None, 1, S[:1], S[:1].clone())
