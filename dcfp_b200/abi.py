@@ -19,10 +19,9 @@ NCHW, NHWC = 0, 1
 class LayerDesc(ctypes.Structure):
     """struct dcfp_layer_desc"""
     _fields_ = [("x", ctypes.c_void_p), ("dy", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
-                ("label", ctypes.c_void_p), ("S1", ctypes.c_void_p), ("S2", ctypes.c_void_p), ("cnt", ctypes.c_void_p),
+                ("keys", ctypes.c_void_p), ("S1", ctypes.c_void_p), ("S2", ctypes.c_void_p),
                 ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
-                ("H0", ctypes.c_int32), ("W0", ctypes.c_int32), ("K", ctypes.c_int32), ("dtype", ctypes.c_int32),
-                ("layout", ctypes.c_int32), ("label_dtype", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2)]
+                ("K", ctypes.c_int32), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class GatherDesc(ctypes.Structure):
@@ -53,6 +52,7 @@ def load(path=LIB_PATH):
     lib.dcfp_abi_version.restype = i32
     lib.dcfp_launch_count.restype = i64
     lib.dcfp_launch_count.argtypes = [i32]
+    lib.dcfp_label_keys.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.dcfp_class_stats.argtypes = [ctypes.POINTER(LayerDesc), vp]
     lib.dcfp_class_stats_grouped.argtypes = [ctypes.POINTER(LayerDesc), i32, vp]
     lib.dcfp_eic_update.argtypes = [vp, vp, vp, i32, vp, ctypes.c_float, ctypes.c_float, i32, vp]

@@ -70,8 +70,9 @@ __global__ void bias_comp_kernel(const float* __restrict__ W, int O, int I, int 
 }
 
 int validate_gather(const dcfp_gather_desc& d, int idx) {
-  DCFP_REQUIRE(d.src && d.dst, DCFP_EINVAL, "channel_gather[%d]: null src/dst", idx);
   DCFP_REQUIRE(d.n_out >= 0 && d.n_in >= 0 && d.I > 0 && d.khw > 0, DCFP_EINVAL, "channel_gather[%d]: bad extents", idx);
+  const bool empty = d.n_out == 0 || d.n_in == 0;
+  DCFP_REQUIRE(empty || (d.src && d.dst), DCFP_EINVAL, "channel_gather[%d]: null src/dst", idx);
   DCFP_REQUIRE(d.in_idx != nullptr || d.n_in == d.I, DCFP_EINVAL, "channel_gather[%d]: in_idx NULL requires n_in == I", idx);
   return 0;
 }

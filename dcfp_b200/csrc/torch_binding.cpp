@@ -39,8 +39,8 @@ int label_dtype_of(const Tensor& label) {
 
 // Fills one descriptor; keeps nothing alive (the caller holds the tensors).
 dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const optional<Tensor>& scale,
-                          const optional<Tensor>& shift, const optional<Tensor>& label, const Tensor& S1, const Tensor& S2,
-                          const optional<Tensor>& cnt, int64_t K) {
+                          const optional<Tensor>& shift, const optional<Tensor>& keys, const Tensor& S1, const Tensor& S2,
+                          int64_t K) {
   require_cuda(x, "x");
   TORCH_CHECK(x.dim() == 4, "dcfp: feature map must be 4-D [N,C,h,w], got ", x.dim(), "-D");
   TORCH_CHECK(x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16, "dcfp: feature map must be fp32 or bf16");
@@ -72,14 +72,13 @@ dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const opt
   };
   d.scale = per_channel(scale, "scale");
   d.shift = per_channel(shift, "shift");
-  if (label.has_value()) {
-    const Tensor& l = *label;
-    require_cuda(l, "label");
-    TORCH_CHECK(l.dim() == 3 && l.size(0) == x.size(0) && l.is_contiguous(), "dcfp: label must be contiguous [N,H0,W0]");
-    d.label = l.data_ptr();
-    d.label_dtype = label_dtype_of(l);
-    d.H0 = static_cast<int32_t>(l.size(1));
-    d.W0 = static_cast<int32_t>(l.size(2));
+  if (keys.has_value()) {
+    const Tensor& k = *keys;
+    require_cuda(k, "keys");
+    TORCH_CHECK(k.scalar_type() == at::kByte && k.is_contiguous() && k.dim() == 3 && k.size(0) == x.size(0) &&
+                    k.size(1) == x.size(2) && k.size(2) == x.size(3),
+                "dcfp: keys must be a contiguous uint8 [N,h,w] tensor at the feature map's resolution (dcfp::label_keys)");
+    d.keys = k.data_ptr<uint8_t>();
   }
   auto arena = [&](const Tensor& t, const char* name, int64_t numel) -> double* {
     require_cuda(t, name);
@@ -89,35 +88,53 @@ dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const opt
   };
   d.S1 = arena(S1, "S1", K * x.size(1));
   d.S2 = arena(S2, "S2", K * x.size(1));
-  if (cnt.has_value()) d.cnt = arena(*cnt, "cnt", K);
   return d;
 }
 
+// keys[N,h,w] (uint8) from label[N,H0,W0]; cnt[K] += pixels per class (optional)
+Tensor label_keys(const Tensor& label, int64_t h, int64_t w, int64_t K, optional<Tensor> cnt) {
+  require_cuda(label, "label");
+  TORCH_CHECK(label.dim() == 3 && label.is_contiguous(), "dcfp::label_keys: label must be contiguous [N,H0,W0]");
+  Tensor keys = at::empty({label.size(0), h, w}, label.options().dtype(at::kByte));
+  double* cp = nullptr;
+  if (cnt.has_value()) {
+    require_cuda(*cnt, "cnt");
+    TORCH_CHECK(cnt->scalar_type() == at::kDouble && cnt->is_contiguous() && cnt->numel() == K,
+                "dcfp::label_keys: cnt must be a contiguous fp64 [K] tensor");
+    cp = cnt->data_ptr<double>();
+  }
+  c10::cuda::CUDAGuard guard(label.device());
+  check_rc(dcfp_label_keys(label.data_ptr(), label_dtype_of(label), static_cast<int>(label.size(0)),
+                           static_cast<int>(label.size(1)), static_cast<int>(label.size(2)), static_cast<int>(h),
+                           static_cast<int>(w), static_cast<int>(K), keys.data_ptr<uint8_t>(), cp, cur_stream()),
+           "label_keys");
+  return keys;
+}
+
 void class_stats(const Tensor& x, const optional<Tensor>& dy, const optional<Tensor>& scale, const optional<Tensor>& shift,
-                 const optional<Tensor>& label, Tensor S1, Tensor S2, optional<Tensor> cnt, int64_t K) {
-  const dcfp_layer_desc d = make_desc(x, dy, scale, shift, label, S1, S2, cnt, K);
+                 const optional<Tensor>& keys, Tensor S1, Tensor S2, int64_t K) {
+  const dcfp_layer_desc d = make_desc(x, dy, scale, shift, keys, S1, S2, K);
   c10::cuda::CUDAGuard guard(x.device());
   check_rc(dcfp_class_stats(&d, cur_stream()), "class_stats");
 }
 
+// keys: one tensor per layer (layers of equal resolution pass the same tensor), or empty when K == 1
 void class_stats_grouped(at::TensorList xs, at::TensorList dys, at::TensorList scales, at::TensorList shifts,
-                         const optional<Tensor>& label, at::TensorList S1s, at::TensorList S2s, at::TensorList cnts,
-                         int64_t K) {
+                         at::TensorList keys, at::TensorList S1s, at::TensorList S2s, int64_t K) {
   const size_t n = xs.size();
   TORCH_CHECK(n > 0, "dcfp::class_stats_grouped: empty layer list");
   TORCH_CHECK(S1s.size() == n && S2s.size() == n, "dcfp::class_stats_grouped: S1/S2 lists must match xs");
   TORCH_CHECK(dys.empty() || dys.size() == n, "dcfp::class_stats_grouped: dys must be empty or match xs");
   TORCH_CHECK(scales.size() == shifts.size() && (scales.empty() || scales.size() == n),
               "dcfp::class_stats_grouped: scales/shifts must be empty or match xs");
-  TORCH_CHECK(cnts.empty() || cnts.size() == n, "dcfp::class_stats_grouped: cnts must be empty or match xs");
+  TORCH_CHECK(keys.empty() || keys.size() == n, "dcfp::class_stats_grouped: keys must be empty or match xs");
   std::vector<dcfp_layer_desc> descs(n);
   for (size_t i = 0; i < n; ++i) {
     optional<Tensor> dy = dys.empty() ? optional<Tensor>() : optional<Tensor>(dys[i]);
     optional<Tensor> sc = scales.empty() ? optional<Tensor>() : optional<Tensor>(scales[i]);
     optional<Tensor> sf = shifts.empty() ? optional<Tensor>() : optional<Tensor>(shifts[i]);
-    // an empty tensor in `cnts` means "do not count for this layer"
-    optional<Tensor> ct = (cnts.empty() || cnts[i].numel() == 0) ? optional<Tensor>() : optional<Tensor>(cnts[i]);
-    descs[i] = make_desc(xs[i], dy, sc, sf, label, S1s[i], S2s[i], ct, K);
+    optional<Tensor> ky = keys.empty() ? optional<Tensor>() : optional<Tensor>(keys[i]);
+    descs[i] = make_desc(xs[i], dy, sc, sf, ky, S1s[i], S2s[i], K);
   }
   c10::cuda::CUDAGuard guard(xs[0].device());
   for (size_t first = 0; first < n; first += DCFP_MAX_GROUP_LAYERS) {
@@ -239,6 +256,7 @@ Tensor channel_gather(const Tensor& src, const optional<Tensor>& out_idx, const 
   Tensor dst = at::empty(gathered_sizes(src, out_idx, in_idx), src.options());
   const int n_out = static_cast<int>(dst.size(0));
   const int n_in = src.dim() >= 2 ? static_cast<int>(dst.size(1)) : 1;
+  if (dst.numel() == 0) return dst;  // empty selection: nothing to launch
   c10::cuda::CUDAGuard guard(src.device());
   check_rc(dcfp_channel_gather(src.data_ptr(), dst.data_ptr(), idx_ptr(out_idx, "out_idx"), n_out, idx_ptr(in_idx, "in_idx"), n_in,
                                static_cast<int>(g.I), static_cast<int>(g.khw), es, cur_stream()),
@@ -302,13 +320,12 @@ int64_t abi_version() { return dcfp_abi_version(); }
 }  // namespace
 
 TORCH_LIBRARY(dcfp, m) {
+  m.def("label_keys(Tensor label, int h, int w, int K, Tensor(a!)? cnt) -> Tensor", &label_keys);
+  m.def("class_stats(Tensor x, Tensor? dy, Tensor? scale, Tensor? shift, Tensor? keys, Tensor(a!) S1, Tensor(b!) S2, int K) -> ()",
+        &class_stats);
   m.def(
-      "class_stats(Tensor x, Tensor? dy, Tensor? scale, Tensor? shift, Tensor? label, Tensor(a!) S1, Tensor(b!) S2, "
-      "Tensor(c!)? cnt, int K) -> ()",
-      &class_stats);
-  m.def(
-      "class_stats_grouped(Tensor[] xs, Tensor[] dys, Tensor[] scales, Tensor[] shifts, Tensor? label, Tensor(a!)[] S1s, "
-      "Tensor(b!)[] S2s, Tensor(c!)[] cnts, int K) -> ()",
+      "class_stats_grouped(Tensor[] xs, Tensor[] dys, Tensor[] scales, Tensor[] shifts, Tensor[] keys, Tensor(a!)[] S1s, "
+      "Tensor(b!)[] S2s, int K) -> ()",
       &class_stats_grouped);
   m.def("reduce_classes(Tensor S1) -> Tensor", &reduce_classes);
   m.def("eic_update(Tensor[] grads, Tensor[] gammas, Tensor offsets, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",

@@ -38,15 +38,21 @@ def launch_count(reset=False):
 
 
 # ---- K1 ----------------------------------------------------------------------------------------
-def class_stats(x, label, K, S1, S2, cnt=None, dy=None, scale=None, shift=None):
-    """S1[k,c] += sum v, S2[k,c] += sum v*v, cnt[k] += #px over pixels whose nearest-down-sampled label is k."""
-    load().class_stats(x, dy, scale, shift, label, S1, S2, cnt, int(K))
+def label_keys(label, h, w, K, cnt=None):
+    """uint8 class keys [N,h,w] (legacy-nearest down-sampling; labels outside [0,K) -> K = dropped);
+    cnt[k] += pixels of class k (fp64, optional)."""
+    return load().label_keys(label, int(h), int(w), int(K), cnt)
 
 
-def class_stats_grouped(xs, label, K, S1s, S2s, cnts=None, dys=None, scales=None, shifts=None):
-    """One launch over many resident feature maps (same dtype / K / functor)."""
-    load().class_stats_grouped(list(xs), list(dys or []), list(scales or []), list(shifts or []), label, list(S1s), list(S2s),
-                               list(cnts or []), int(K))
+def class_stats(x, keys, K, S1, S2, dy=None, scale=None, shift=None):
+    """S1[k,c] += sum v, S2[k,c] += sum v*v over the pixels whose class key is k (keys from label_keys)."""
+    load().class_stats(x, dy, scale, shift, keys, S1, S2, int(K))
+
+
+def class_stats_grouped(xs, keys, K, S1s, S2s, dys=None, scales=None, shifts=None):
+    """One launch over many resident feature maps (same dtype / K / functor); keys: one tensor per layer."""
+    load().class_stats_grouped(list(xs), list(dys or []), list(scales or []), list(shifts or []), list(keys or []), list(S1s),
+                               list(S2s), int(K))
 
 
 def reduce_classes(S1):

@@ -46,37 +46,41 @@ extern "C" {
 #define DCFP_MAX_CLASSES 255
 #define DCFP_MAX_GROUP_LAYERS 160
 
+/* ---- label keys: nearest down-sampling of the label map, once per label resolution --------------
+ * keys[n][i][j] = label[n][min(floor(i * (float)H0 / h), H0-1)][min(floor(j * (float)W0 / w), W0-1)]
+ * (legacy `nearest` of F.interpolate, evaluated in registers -- no float label tensor is ever
+ * materialised); a label outside [0, K) -- e.g. the ignore label 255 -- becomes the key K
+ * ("dropped").  cnt[k] += number of pixels of class k at this resolution (fp64; may be NULL).
+ * Reference counterpart of the count: np.bincount in datasets/Base.py:78.                       */
+int dcfp_label_keys(const void* label, int label_dtype, int N, int H0, int W0, int h, int w, int K, uint8_t* keys,
+                    double* cnt, void* stream);
+
 /*
  * One scored feature map (one BN layer of one micro-batch).
  *
- * value functor, per element of channel c at pixel p (n, i, j):
+ * value functor, per element of channel c at pixel p:
  *   forward  (dy == NULL):  v = x * scale[c] + shift[c]            (scale/shift NULL -> 1 / 0)
  *   backward (dy != NULL):  v = dy * (x * scale[c] + shift[c])     with scale = invstd,
  *                           shift = -mean * invstd  => v = dy * xhat, and
  *                           sum_k S1[k][c] == d(loss)/d(gamma_c)   (BN backward, the quantity
  *                           pruners/dcfp_pruner.py:18 reads as m.weight.grad)
- * class key:  k = label[n][min(floor(i * (float)H0 / h), H0-1)][min(floor(j * (float)W0 / w), W0-1)]
- *             (legacy `nearest` of F.interpolate); k outside [0, K) -- e.g. the ignore label 255 --
- *             is dropped.  label == NULL puts every pixel in class 0 (K must be 1).
- * accumulates (+=, fp64):  S1[k*C + c] += sum v,  S2[k*C + c] += sum v*v,  cnt[k] += #pixels
- *             (cnt may be NULL; pass it for ONE layer per label resolution).
+ * class key:  keys[n][p] from dcfp_label_keys at this layer's (h, w); key >= K is dropped.
+ *             keys == NULL puts every pixel in class 0 (K must be 1).
+ * accumulates (+=, fp64):  S1[k*C + c] += sum v,  S2[k*C + c] += sum v*v
  */
 typedef struct dcfp_layer_desc {
-  const void* x;      /* [N,C,h,w] (NCHW) or [N,h,w,C] (NHWC), dtype `dtype` */
-  const void* dy;     /* same shape/dtype as x, or NULL */
-  const float* scale; /* [C] or NULL */
-  const float* shift; /* [C] or NULL */
-  const void* label;  /* [N,H0,W0] of label_dtype, or NULL */
-  double* S1;         /* [K,C] */
-  double* S2;         /* [K,C] */
-  double* cnt;        /* [K] or NULL */
+  const void* x;       /* [N,C,h,w] (NCHW) or [N,h,w,C] (NHWC), dtype `dtype` */
+  const void* dy;      /* same shape/dtype as x, or NULL */
+  const float* scale;  /* [C] or NULL */
+  const float* shift;  /* [C] or NULL */
+  const uint8_t* keys; /* [N,h,w] class keys, or NULL */
+  double* S1;          /* [K,C] */
+  double* S2;          /* [K,C] */
   int32_t N, C, h, w;
-  int32_t H0, W0;
   int32_t K;
-  int32_t dtype;       /* DCFP_F32 | DCFP_BF16 */
-  int32_t layout;      /* DCFP_NCHW | DCFP_NHWC */
-  int32_t label_dtype; /* DCFP_LABEL_* */
-  int32_t reserved[2];
+  int32_t dtype;  /* DCFP_F32 | DCFP_BF16 */
+  int32_t layout; /* DCFP_NCHW | DCFP_NHWC */
+  int32_t reserved;
 } dcfp_layer_desc;
 
 /* ---- K1: label-keyed segmented reduction over conv/BN feature maps -------------------------
@@ -85,7 +89,7 @@ typedef struct dcfp_layer_desc {
  * autograd's BN backward that feeds pruners/dcfp_pruner.py:18.                              */
 int dcfp_class_stats(const dcfp_layer_desc* desc_host, void* stream);
 /* Same, for up to DCFP_MAX_GROUP_LAYERS resident feature maps in ONE launch (all K, dtype,
- * layout, dy-nullness must agree).  Layers only share the grid; outputs stay per layer.      */
+ * dy-nullness must agree).  Layers only share the grid; outputs stay per layer.              */
 int dcfp_class_stats_grouped(const dcfp_layer_desc* descs_host, int n_layers, void* stream);
 
 /* ---- K2a: EIC update -- pruners/dcfp_pruner.py:15-20 ------------------------------------------
