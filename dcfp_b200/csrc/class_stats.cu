@@ -31,14 +31,15 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace dcfp {
 namespace {
 
-constexpr int kWarps = 4;
-constexpr int kThreads = kWarps * 32;
+constexpr int kWarpsPrivate = 4;  // warps per CTA when every warp owns an accumulator table (small K)
+constexpr int kWarpsShared = 8;   // warps per CTA sharing one table through shared atomics (large K)
 constexpr int kBoxRowBytes = 128;                 // SWIZZLE_128B span
 constexpr int kBoxBytes = 32 * kBoxRowBytes;      // one [32 channels x 128 B] box = 4 KB
 constexpr int kGroups = kBoxRowBytes / 16;        // 128-bit groups per row (8)
@@ -63,6 +64,7 @@ struct GroupParams {
   int32_t tile_prefix[MAXL + 1];
   int32_t n_layers;
   int32_t K;
+  int32_t stages;
 };
 constexpr int kSmallGroup = 4;
 constexpr int kBigGroupFwd = 160;  // 160 * (128 + 64) B  = 30.0 KB  (< 32 KB parameter space)
@@ -124,73 +126,49 @@ struct Elem<__nv_bfloat16> {
   }
 };
 
-// Flush one finished run of one lane (= one channel) into the shared accumulators.  Out of line:
-// it sits on the rare path (key change) and would otherwise be replicated in the unrolled loop.
+// acc[key][lane] += (a1, a2): the shared accumulator is an interleaved float2 [K][32] table, so one
+// 64-bit load / FADD2 / 64-bit store updates both moments of (class, channel).  Lanes touch
+// consecutive 8-byte slots: conflict-free.
 template <bool SHARED_ACC>
-__device__ __noinline__ void flush_run(float* acc1, float* acc2, unsigned* seen, unsigned cur, int lane, float a1, float a2) {
-  if (SHARED_ACC) {
-    atomicAdd(&acc1[cur * 32 + lane], a1);
-    atomicAdd(&acc2[cur * 32 + lane], a2);
-  } else {
-    acc1[cur * 32 + lane] += a1;
-    acc2[cur * 32 + lane] += a2;
+__device__ __forceinline__ void acc_add(uint32_t acc_lane, unsigned key, float a1, float a2) {
+  const uint32_t addr = acc_lane + key * 256u;
+  if (SHARED_ACC) {  // one CTA-wide table (large K): shared-memory atomics
+    float* p = reinterpret_cast<float*>(__cvta_shared_to_generic(addr));
+    atomicAdd(p, a1);
+    atomicAdd(p + 1, a2);
+  } else {  // per-warp table: plain read-modify-write
+    f2 cur;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cur) : "r"(addr));
+    cur = add2(cur, pack2(a1, a2));
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(cur) : "memory");
   }
-  if (lane == 0) seen[cur] = 1u;
 }
 
-// Run-length accumulator of one lane; everything except the partial sums is warp-uniform.
-template <bool SHARED_ACC>
-struct RunAcc {
-  f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;  // packed partial sums of the current run
-  unsigned cur, curw;
-  float* acc1;
-  float* acc2;
-  unsigned* seen;
-  int K, lane;
-
-  __device__ __forceinline__ void flush() {
-    if (cur < static_cast<unsigned>(K)) {
-      const f2 t1 = add2(s1a, s1b), t2 = add2(s2a, s2b);
-      flush_run<SHARED_ACC>(acc1, acc2, seen, cur, lane, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
-    }
-    s1a = s1b = s2a = s2b = 0;
+// value of one pixel re-read from the staged box (per-pixel path of a quad that straddles a class
+// boundary; a rolled loop keeps this code to one site)
+template <typename T, bool BWD, bool AFFINE>
+__device__ __forceinline__ float load_px(uint32_t addr, float sc, float sf) {
+  float x, d = 1.f;
+  if (sizeof(T) == 4) {
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+    if (BWD) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(addr + kBoxBytes));
+  } else {
+    unsigned short hx, hd = 0;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(addr));
+    if (BWD) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hd) : "r"(addr + kBoxBytes));
+    x = __uint_as_float(static_cast<unsigned>(hx) << 16);
+    d = __uint_as_float(static_cast<unsigned>(hd) << 16);
   }
-  __device__ __forceinline__ void add_pair_fast(f2 p, f2 q) {  // 4 px of the current run
-    s1a = add2(s1a, p);
-    s1b = add2(s1b, q);
-    s2a = fma2(p, p, s2a);
-    s2b = fma2(q, q, s2b);
-  }
-  __device__ __forceinline__ void add_px(float v, unsigned key) {
-    if (key != cur) {
-      flush();
-      cur = key;
-      curw = key * 0x01010101u;
-    }
-    const f2 pv = pack2(v, 0.f);
-    s1a = add2(s1a, pv);
-    s2a = fma2(pv, pv, s2a);
-  }
-  // four consecutive pixels (two pairs) with packed keys `wv` (one byte each, warp-uniform)
-  __device__ __forceinline__ void add4(f2 p, f2 q, unsigned wv) {
-    if (wv == curw) {
-      add_pair_fast(p, q);
-    } else {
-      add_px(lo2(p), wv & 0xffu);
-      add_px(hi2(p), (wv >> 8) & 0xffu);
-      add_px(lo2(q), (wv >> 16) & 0xffu);
-      add_px(hi2(q), wv >> 24);
-    }
-  }
-};
+  if (BWD) return d * fmaf(x, sc, sf);
+  return AFFINE ? fmaf(x, sc, sf) : x;
+}
 
 template <typename T, bool BWD, bool AFFINE>
-__device__ __forceinline__ void load_group(uint32_t row, int g, int lane, f2 sc2, f2 sf2, f2* v) {
-  const uint32_t off = static_cast<uint32_t>((g ^ (lane & 7)) << 4);  // SWIZZLE_128B: chunk ^= row % 8
-  Elem<T>::unpack(lds128(row + off), v);
+__device__ __forceinline__ void load_group(uint32_t addr, f2 sc2, f2 sf2, f2* v) {
+  Elem<T>::unpack(lds128(addr), v);
   if (BWD) {
     f2 d[Elem<T>::kPairs];
-    Elem<T>::unpack(lds128(row + kBoxBytes + off), d);
+    Elem<T>::unpack(lds128(addr + kBoxBytes), d);
 #pragma unroll
     for (int q = 0; q < Elem<T>::kPairs; ++q) v[q] = mul2(d[q], fma2(v[q], sc2, sf2));
   } else if (AFFINE) {
@@ -199,131 +177,192 @@ __device__ __forceinline__ void load_group(uint32_t row, int g, int lane, f2 sc2
   }
 }
 
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int STAGES>
-__device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMap* maps, const int K, const int tile,
-                                             unsigned char* smem) {
+// position of a warp's it-th box inside the layer, advanced without divisions
+struct BoxCursor {
+  int n, b;  // plane, box inside the plane
+  __device__ __forceinline__ void advance(int step, int boxes_per_plane) {
+    b += step;
+    while (b >= boxes_per_plane) {
+      b -= boxes_per_plane;
+      ++n;
+    }
+  }
+};
+
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS>
+__device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMap* maps, const int K, const int stages,
+                                             const int tile, unsigned char* smem) {
   constexpr int kBoxPx = kBoxRowBytes / static_cast<int>(sizeof(T));  // 32 (fp32) / 64 (bf16)
-  constexpr int kWords = kBoxPx / 4;                                  // packed key words per box
+  constexpr int kWords = kBoxPx / 4;                                  // packed key words (quads) per box
+  constexpr int kQuadsPerGroup = kWords / kGroups;                    // 1 (fp32) / 2 (bf16)
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int kAccCopies = SHARED_ACC ? 1 : kWarps;
+  constexpr int kAccCopies = SHARED_ACC ? 1 : WARPS;
   constexpr int kPairs = Elem<T>::kPairs;
+  constexpr int kStageBytes = kTens * kBoxBytes;
+  constexpr int kThreadsT = WARPS * 32;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = tile / L.n_cg, cg = tile - chunk * L.n_cg;
   const int n_active = min(32, L.C - cg * 32);
 
-  // ---- shared-memory carve-up: [boxes | accumulators | seen flags | mbarriers] ------------------
-  unsigned char* bufs = smem;  // [kWarps][STAGES][kTens][kBoxBytes], 1024-B aligned
-  float* acc1 = reinterpret_cast<float*>(smem + static_cast<size_t>(kWarps) * STAGES * kTens * kBoxBytes);
-  float* acc2 = acc1 + kAccCopies * K * 32;
-  unsigned* seen = reinterpret_cast<unsigned*>(acc2 + kAccCopies * K * 32);  // [K]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(seen + ((K + 1) & ~1));
+  // ---- shared-memory carve-up: [boxes | accumulators (float2 [copies][K][32]) | mbarriers] -------
+  unsigned char* bufs = smem;  // [WARPS][stages][kTens][kBoxBytes], 1024-B aligned
+  float2* acc = reinterpret_cast<float2*>(smem + static_cast<size_t>(WARPS) * stages * kStageBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(acc + kAccCopies * K * 32);
 
-  for (int i = tid; i < 2 * kAccCopies * K * 32 + K; i += kThreads) reinterpret_cast<unsigned*>(acc1)[i] = 0u;
-  if (tid < kWarps * STAGES) mbar_init(smem_u32(&bars[tid]), 1);
+  for (int i = tid; i < kAccCopies * K * 32; i += kThreadsT) acc[i] = make_float2(0.f, 0.f);
+  if (tid < WARPS * stages) mbar_init(smem_u32(&bars[tid]), 1);
   mbar_fence_init();
   __syncthreads();
 
   const int box_begin = chunk * L.boxes_per_chunk;
   const int box_end = min(box_begin + L.boxes_per_chunk, L.n_boxes);
+  const int n_my = (box_end - box_begin - warp + WARPS - 1) / WARPS;  // boxes of this warp
   const uint64_t policy = policy_evict_first();
-  const uint32_t my_bufs = smem_u32(bufs + static_cast<size_t>(warp) * STAGES * kTens * kBoxBytes);
-  const uint32_t my_bars = smem_u32(&bars[warp * STAGES]);
+  const uint32_t my_bufs = smem_u32(bufs + static_cast<size_t>(warp) * stages * kStageBytes);
+  const uint32_t my_bars = smem_u32(&bars[warp * stages]);
+  const uint32_t acc_lane = smem_u32(acc + (SHARED_ACC ? 0 : warp * K * 32) + lane);
+  const int row0 = cg * 32;
 
-  auto issue = [&](int it) {  // one elected lane arms the barrier and launches the tile copies
-    const int box = box_begin + warp + it * kWarps;
-    if (box >= box_end || lane != 0) return;
-    const int stage = it % STAGES;
-    const int n = box / L.boxes_per_plane;
-    const int p0 = (box - n * L.boxes_per_plane) * kBoxPx;
-    const uint32_t bar = my_bars + stage * 8;
-    const uint32_t dst = my_bufs + stage * (kTens * kBoxBytes);
-    mbar_expect_tx(bar, kTens * kBoxBytes);
-    tma_load_2d(dst, maps, p0, n * L.C + cg * 32, bar, policy);
-    if (BWD) tma_load_2d(dst + kBoxBytes, maps + 1, p0, n * L.C + cg * 32, bar, policy);
+  BoxCursor issue_at, key_at;
+  issue_at.n = (box_begin + warp) / L.boxes_per_plane;
+  issue_at.b = (box_begin + warp) - issue_at.n * L.boxes_per_plane;
+  key_at = issue_at;
+
+  int issue_it = 0, issue_stage = 0;
+  auto issue = [&]() {  // one elected lane arms the barrier and launches the tile copies
+    if (issue_it < n_my) {
+      if (lane == 0) {
+        const uint32_t bar = my_bars + issue_stage * 8;
+        const uint32_t dst = my_bufs + issue_stage * kStageBytes;
+        mbar_expect_tx(bar, kStageBytes);
+        tma_load_2d(dst, maps, issue_at.b * kBoxPx, issue_at.n * L.C + row0, bar, policy);
+        if (BWD) tma_load_2d(dst + kBoxBytes, maps + 1, issue_at.b * kBoxPx, issue_at.n * L.C + row0, bar, policy);
+      }
+      issue_at.advance(WARPS, L.boxes_per_plane);
+    }
+    ++issue_it;
+    if (++issue_stage == stages) issue_stage = 0;
   };
   // packed class keys of the box's pixels 4*lane .. 4*lane+3 (lanes < kWords); K = "dropped"
-  auto key_word = [&](int it) -> unsigned {
-    const int box = box_begin + warp + it * kWarps;
-    const unsigned dropped = static_cast<unsigned>(K) * 0x01010101u;
-    if (box >= box_end || lane >= kWords) return dropped;
-    const int n = box / L.boxes_per_plane;
-    const int p = (box - n * L.boxes_per_plane) * kBoxPx + 4 * lane;
-    if (p >= L.HW) return dropped;  // HW % 4 == 0: a word is entirely inside or outside the plane
-    if (L.keys == nullptr) return 0u;
-    return __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(n) * L.HW + p));
+  const unsigned dropped = static_cast<unsigned>(K) * 0x01010101u;
+  int key_it = 0;
+  auto key_word = [&]() -> unsigned {
+    unsigned w = dropped;
+    if (key_it < n_my) {
+      const int p = key_at.b * kBoxPx + 4 * lane;  // HW % 4 == 0: a word is entirely inside or outside the plane
+      if (lane < kWords && p < L.HW)
+        w = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(key_at.n) * L.HW + p)) : 0u;
+      key_at.advance(WARPS, L.boxes_per_plane);
+    }
+    ++key_it;
+    return w;
   };
 
   float sc = 1.f, sf = 0.f;
   if (lane < n_active) {
-    if (L.scale) sc = L.scale[cg * 32 + lane];
-    if (L.shift) sf = L.shift[cg * 32 + lane];
+    if (L.scale) sc = L.scale[row0 + lane];
+    if (L.shift) sf = L.shift[row0 + lane];
   }
   const f2 sc2 = pack2(sc, sc), sf2 = pack2(sf, sf);
 
-  RunAcc<SHARED_ACC> ra;
-  ra.K = K;
-  ra.lane = lane;
-  ra.cur = K;
-  ra.curw = static_cast<unsigned>(K) * 0x01010101u;
-  ra.acc1 = acc1 + (SHARED_ACC ? 0 : warp * K * 32);
-  ra.acc2 = acc2 + (SHARED_ACC ? 0 : warp * K * 32);
-  ra.seen = seen;
+  for (int s = 0; s < stages; ++s) issue();
+  unsigned lw = key_word();
 
-#pragma unroll
-  for (int s = 0; s < STAGES; ++s) issue(s);
-  unsigned lw = key_word(0);
+  // SWIZZLE_128B: the 16-B chunk index of row r is XORed with r % 8 (lane == row)
+  const uint32_t row_off = static_cast<uint32_t>(lane * kBoxRowBytes);
+  const uint32_t l7 = static_cast<uint32_t>(lane & 7);
 
-  const int n_my = (box_end - box_begin - warp + kWarps - 1) / kWarps;  // boxes of this warp
+  int stage = 0;
+  uint32_t parity = 0;
   for (int it = 0; it < n_my; ++it) {
-    const unsigned lw_next = key_word(it + 1);  // global load overlaps the wait below
-    const int stage = it % STAGES;
-    mbar_wait(my_bars + stage * 8, (it / STAGES) & 1);
-    const uint32_t row = my_bufs + stage * (kTens * kBoxBytes) + lane * kBoxRowBytes;
-    const bool uniform = __all_sync(0xffffffffu, lane >= kWords || lw == ra.curw);
-    if (uniform) {  // the whole box continues the current run: branch-free
+    const unsigned lw_next = key_word();  // global load overlaps the wait below
+    mbar_wait(my_bars + stage * 8, parity);
+    const uint32_t box = my_bufs + stage * kStageBytes + row_off;
+    const unsigned w0 = __shfl_sync(0xffffffffu, lw, 0);
+    const unsigned key0 = w0 & 0xffu;
+    const bool uniform = __all_sync(0xffffffffu, lane >= kWords || lw == key0 * 0x01010101u);
+    if (uniform) {
+      // every pixel of the box has the same class: branch-free packed accumulate, one table update
+      if (key0 < static_cast<unsigned>(K)) {
+        f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
 #pragma unroll
-      for (int g = 0; g < kGroups; ++g) {
-        f2 v[kPairs];
-        load_group<T, BWD, AFFINE>(row, g, lane, sc2, sf2, v);
+        for (int g = 0; g < kGroups; ++g) {
+          f2 v[kPairs];
+          load_group<T, BWD, AFFINE>(box + ((g ^ l7) << 4), sc2, sf2, v);
 #pragma unroll
-        for (int h = 0; h < kPairs / 2; ++h) ra.add_pair_fast(v[2 * h], v[2 * h + 1]);
+          for (int h = 0; h < kPairs / 2; ++h) {
+            s1a = add2(s1a, v[2 * h]);
+            s1b = add2(s1b, v[2 * h + 1]);
+            s2a = fma2(v[2 * h], v[2 * h], s2a);
+            s2b = fma2(v[2 * h + 1], v[2 * h + 1], s2b);
+          }
+        }
+        s1a = add2(s1a, s1b);
+        s2a = add2(s2a, s2b);
+        acc_add<SHARED_ACC>(acc_lane, key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
       }
     } else {
-#pragma unroll
+      // a class boundary crosses the box: per quad (4 px, one packed key word) -- a quad with one
+      // class is summed in registers and added to the table; a straddling quad goes pixel by pixel
+#pragma unroll 1
       for (int g = 0; g < kGroups; ++g) {
+        const uint32_t gaddr = box + ((static_cast<uint32_t>(g) ^ l7) << 4);
         f2 v[kPairs];
-        load_group<T, BWD, AFFINE>(row, g, lane, sc2, sf2, v);
+        load_group<T, BWD, AFFINE>(gaddr, sc2, sf2, v);
 #pragma unroll
-        for (int h = 0; h < kPairs / 2; ++h)
-          ra.add4(v[2 * h], v[2 * h + 1], __shfl_sync(0xffffffffu, lw, g * (kPairs / 2) + h));
+        for (int h = 0; h < kQuadsPerGroup; ++h) {
+          const unsigned wv = __shfl_sync(0xffffffffu, lw, g * kQuadsPerGroup + h);
+          const unsigned key = wv & 0xffu;
+          if (wv == key * 0x01010101u) {
+            if (key < static_cast<unsigned>(K)) {
+              const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
+              const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
+              acc_add<SHARED_ACC>(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+            }
+          } else {
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+              const unsigned ke = (wv >> (8 * e)) & 0xffu;
+              if (ke < static_cast<unsigned>(K)) {
+                const float x = load_px<T, BWD, AFFINE>(gaddr + (h * 4 + e) * static_cast<int>(sizeof(T)), sc, sf);
+                acc_add<SHARED_ACC>(acc_lane, ke, x, x * x);
+              }
+            }
+          }
+        }
       }
     }
     __syncwarp();
-    issue(it + STAGES);  // refill the stage just consumed
+    issue();  // refill the stage just consumed
     lw = lw_next;
+    if (++stage == stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
   }
-  ra.flush();
   __syncthreads();
 
-  // ---- CTA partials -> fp64 arena (coalesced RED.F64; only classes this CTA met) ----------------
-  for (int idx = tid; idx < K * 32; idx += kThreads) {
+  // ---- CTA partials -> fp64 arena (coalesced RED.F64; zero partials are skipped) ----------------
+  for (int idx = tid; idx < K * 32; idx += kThreadsT) {
     const int k = idx >> 5, cl = idx & 31;
-    if (seen[k] == 0u || cl >= n_active) continue;
+    if (cl >= n_active) continue;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int w = 0; w < kAccCopies; ++w) {
-      s1 += acc1[w * K * 32 + idx];
-      s2 += acc2[w * K * 32 + idx];
+      const float2 a = acc[w * K * 32 + idx];
+      s1 += a.x;
+      s2 += a.y;
     }
-    const size_t o = static_cast<size_t>(k) * L.C + cg * 32 + cl;
+    if (s1 == 0.f && s2 == 0.f) continue;  // class not met by this CTA (or all-zero values): nothing to add
+    const size_t o = static_cast<size_t>(k) * L.C + row0 + cl;
     atomicAdd(&L.S1[o], static_cast<double>(s1));
     atomicAdd(&L.S2[o], static_cast<double>(s2));
   }
 }
 
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int STAGES, int MAXL>
-__global__ void __launch_bounds__(kThreads, 4)
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL>
+__global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
     class_stats_kernel(const __grid_constant__ GroupParams<MAXL, BWD ? 2 : 1> P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned; SWIZZLE_128B boxes need 1024 B
@@ -335,7 +374,8 @@ __global__ void __launch_bounds__(kThreads, 4)
     if (P.tile_prefix[mid] <= tile) lo = mid;
     else hi = mid;
   }
-  process_tile<T, BWD, AFFINE, SHARED_ACC, STAGES>(P.L[lo], &P.maps[lo * (BWD ? 2 : 1)], P.K, tile - P.tile_prefix[lo], smem);
+  process_tile<T, BWD, AFFINE, SHARED_ACC, WARPS>(P.L[lo], &P.maps[lo * (BWD ? 2 : 1)], P.K, P.stages, tile - P.tile_prefix[lo],
+                                                  smem);
 }
 
 // Generic path: any extent / alignment / layout (tiny 1x1..6x6 maps, odd crops, NHWC).  One
@@ -450,9 +490,10 @@ int make_map(CUtensorMap* map, const void* base, int dtype, long long rows, long
 }
 
 size_t tile_smem_bytes(int K, bool bwd, bool shared_acc, int stages) {
-  const int copies = shared_acc ? 1 : kWarps;
-  return static_cast<size_t>(kWarps) * stages * (bwd ? 2 : 1) * kBoxBytes + static_cast<size_t>(2) * copies * K * 32 * 4 +
-         static_cast<size_t>((K + 1) & ~1) * 4 + 8 * kWarps * stages + 1024 /* base alignment slack */;
+  const int warps = shared_acc ? kWarpsShared : kWarpsPrivate;
+  const int copies = shared_acc ? 1 : warps;
+  return static_cast<size_t>(warps) * stages * (bwd ? 2 : 1) * kBoxBytes + static_cast<size_t>(copies) * K * 32 * 8 +
+         8 * warps * stages + 1024 /* base alignment slack */;
 }
 
 int validate(const dcfp_layer_desc& d, int idx) {
@@ -491,13 +532,24 @@ int launch_generic(const dcfp_layer_desc& d, cudaStream_t stream) {
   return finish_launch("class_stats_generic");
 }
 
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int STAGES, int MAXL>
-int launch_tiled(const GroupParams<MAXL, BWD ? 2 : 1>& P, int n_tiles, cudaStream_t stream) {
-  const size_t smem = tile_smem_bytes(P.K, BWD, SHARED_ACC, STAGES);
-  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, STAGES, MAXL>;
+// pipeline depth: 2 stages per warp keeps the most warps resident (measured best); override for tuning
+int pick_stages() {
+  static const int forced = []() {
+    const char* e = getenv("DCFP_K1_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  return (forced >= 2 && forced <= 8) ? forced : 2;
+}
+
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int MAXL>
+int launch_tiled(GroupParams<MAXL, BWD ? 2 : 1>& P, int n_tiles, cudaStream_t stream) {
+  constexpr int kWarpsT = SHARED_ACC ? kWarpsShared : kWarpsPrivate;
+  P.stages = pick_stages();
+  const size_t smem = tile_smem_bytes(P.K, BWD, SHARED_ACC, P.stages);
+  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
-  kern<<<n_tiles, kThreads, smem, stream>>>(P);
+  kern<<<n_tiles, kWarpsT * 32, smem, stream>>>(P);
   return finish_launch("class_stats");
 }
 
@@ -536,11 +588,11 @@ int run_tiled(const dcfp_layer_desc* descs, const int* which, int n, int boxes_p
   const int n_tiles = P.tile_prefix[n];
   if (n_tiles == 0) return 0;
   if (K > kPrivateAccMaxK) {  // one CTA-wide accumulator copy, shared atomics; [K x 32 x 2] floats
-    if (BWD || affine) return launch_tiled<T, BWD, true, true, 2, MAXL>(P, n_tiles, stream);
-    return launch_tiled<T, BWD, false, true, 2, MAXL>(P, n_tiles, stream);
+    if (BWD || affine) return launch_tiled<T, BWD, true, true, MAXL>(P, n_tiles, stream);
+    return launch_tiled<T, BWD, false, true, MAXL>(P, n_tiles, stream);
   }
-  if (BWD || affine) return launch_tiled<T, BWD, true, false, 2, MAXL>(P, n_tiles, stream);
-  return launch_tiled<T, BWD, false, false, 2, MAXL>(P, n_tiles, stream);
+  if (BWD || affine) return launch_tiled<T, BWD, true, false, MAXL>(P, n_tiles, stream);
+  return launch_tiled<T, BWD, false, false, MAXL>(P, n_tiles, stream);
 }
 
 int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
