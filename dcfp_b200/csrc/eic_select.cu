@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kMaskThreads) layer_mask_kernel(const float* _
   __shared__ int s_count;
   const int l = blockIdx.x;
   const int beg = layer_off[l], C = layer_off[l + 1] - beg;
-  const float t = thresh[layer_group[l]];
+  const float t = thresh[layer_group[l] & 1];  // groups 2/3: masked with thresh[0/1] but not part of the threshold set
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   int local = 0;

@@ -108,7 +108,8 @@ int dcfp_reduce_classes(const double* S1, int K, int C, float* out, void* stream
 /* ---- K2b: global threshold + keep masks -- pruners/dcfp_pruner.py:43-92 ------------------------
  * score: concatenated fp32 scores of the n_layers scored layers; layer l owns
  * [layer_off[l], layer_off[l+1]) and belongs to group layer_group[l] in {0,1}
- * (get_bn_group, :36-37).  thresh[g] = k_idx[g]-th smallest score of group g (ascending, 0-based;
+ * (get_bn_group, :36-37); the values 2/3 mean "masked with thresh[0/1] but excluded from the
+ * threshold set" (a BN in except_layers whose conv is not, :45 vs :73).  thresh[g] = k_idx[g]-th smallest score of group g (ascending, 0-based;
  * get_thresh :59-64; k_idx[g] < 0 -> group empty, thresh 0).  mask = score > thresh (strict,
  * :77); a layer with fewer than min_keep[l] survivors additionally keeps its min_keep[l]
  * highest-scoring channels, ties broken lowest-index-first (:79-82; torch.sort's tie order is
