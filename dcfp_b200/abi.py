@@ -21,7 +21,7 @@ class LayerDesc(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("dy", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
                 ("keys", ctypes.c_void_p), ("S1", ctypes.c_void_p), ("S2", ctypes.c_void_p),
                 ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
-                ("K", ctypes.c_int32), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("K", ctypes.c_int32), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32), ("ld", ctypes.c_int32)]
 
 
 class GatherDesc(ctypes.Structure):

@@ -52,7 +52,7 @@ struct LayerDev {
   const float* shift;
   double* S1;
   double* S2;
-  int32_t C, HW, n_cg;
+  int32_t C, HW, n_cg, ld;
   int32_t boxes_per_plane, n_boxes, boxes_per_chunk;
 };
 
@@ -355,7 +355,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
       s2 += a.y;
     }
     if (s1 == 0.f && s2 == 0.f) continue;  // class not met by this CTA (or all-zero values): nothing to add
-    const size_t o = static_cast<size_t>(k) * L.C + row0 + cl;
+    const size_t o = static_cast<size_t>(k) * L.ld + row0 + cl;
     atomicAdd(&L.S1[o], static_cast<double>(s1));
     atomicAdd(&L.S2[o], static_cast<double>(s2));
   }
@@ -388,7 +388,7 @@ struct GenericLayer {
   const float* shift;
   double* S1;
   double* S2;
-  int32_t C, HW;
+  int32_t C, HW, ld;
 };
 template <typename T, bool BWD>
 __global__ void class_stats_generic_kernel(const GenericLayer L, const int K, const int nhwc, const int px_per_block) {
@@ -403,8 +403,8 @@ __global__ void class_stats_generic_kernel(const GenericLayer L, const int K, co
   unsigned cur = K;
   auto flush = [&]() {
     if (cur < static_cast<unsigned>(K)) {
-      atomicAdd(&L.S1[static_cast<size_t>(cur) * L.C + c], static_cast<double>(a1));
-      atomicAdd(&L.S2[static_cast<size_t>(cur) * L.C + c], static_cast<double>(a2));
+      atomicAdd(&L.S1[static_cast<size_t>(cur) * L.ld + c], static_cast<double>(a1));
+      atomicAdd(&L.S2[static_cast<size_t>(cur) * L.ld + c], static_cast<double>(a2));
     }
     a1 = a2 = 0.f;
   };
@@ -504,6 +504,7 @@ int validate(const dcfp_layer_desc& d, int idx) {
                DCFP_MAX_CLASSES);
   DCFP_REQUIRE(d.dtype == DCFP_F32 || d.dtype == DCFP_BF16, DCFP_EINVAL, "class_stats[%d]: unknown dtype %d", idx, d.dtype);
   DCFP_REQUIRE(d.layout == DCFP_NCHW || d.layout == DCFP_NHWC, DCFP_EINVAL, "class_stats[%d]: unknown layout %d", idx, d.layout);
+  DCFP_REQUIRE(d.ld == 0 || d.ld >= d.C, DCFP_EINVAL, "class_stats[%d]: ld=%d < C=%d", idx, d.ld, d.C);
   DCFP_REQUIRE(d.keys != nullptr || d.K == 1, DCFP_EINVAL, "class_stats[%d]: keys == NULL requires K == 1", idx);
   DCFP_REQUIRE(static_cast<long long>(d.h) * d.w < (1LL << 30), DCFP_ETOOBIG, "class_stats[%d]: plane too large", idx);
   DCFP_REQUIRE(static_cast<long long>(d.N) * d.C < (1LL << 31), DCFP_ETOOBIG, "class_stats[%d]: too many planes", idx);
@@ -524,7 +525,7 @@ bool tiled_ok(const dcfp_layer_desc& d) {
 
 template <typename T, bool BWD>
 int launch_generic(const dcfp_layer_desc& d, cudaStream_t stream) {
-  GenericLayer L{d.x, d.dy, d.keys, d.scale, d.shift, d.S1, d.S2, d.C, d.h * d.w};
+  GenericLayer L{d.x, d.dy, d.keys, d.scale, d.shift, d.S1, d.S2, d.C, d.h * d.w, d.ld > 0 ? d.ld : d.C};
   const int threads = 128;
   const int px_per_block = 256;
   dim3 grid((d.C + threads - 1) / threads, (L.HW + px_per_block - 1) / px_per_block, d.N);
@@ -572,6 +573,7 @@ int run_tiled(const dcfp_layer_desc* descs, const int* which, int n, int boxes_p
     L.S1 = d.S1;
     L.S2 = d.S2;
     L.C = d.C;
+    L.ld = d.ld > 0 ? d.ld : d.C;
     L.HW = d.h * d.w;
     L.n_cg = (d.C + 31) / 32;
     L.boxes_per_plane = (L.HW + kBoxPx - 1) / kBoxPx;

@@ -80,14 +80,19 @@ dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const opt
                 "dcfp: keys must be a contiguous uint8 [N,h,w] tensor at the feature map's resolution (dcfp::label_keys)");
     d.keys = k.data_ptr<uint8_t>();
   }
-  auto arena = [&](const Tensor& t, const char* name, int64_t numel) -> double* {
+  // S1/S2: fp64 [K, C], either contiguous or a column slice of a shared [K, sum C] arena
+  auto arena = [&](const Tensor& t, const char* name) -> double* {
     require_cuda(t, name);
-    TORCH_CHECK(t.scalar_type() == at::kDouble && t.is_contiguous() && t.numel() == numel, "dcfp: `", name,
-                "` must be a contiguous fp64 tensor of ", numel, " elements");
+    TORCH_CHECK(t.scalar_type() == at::kDouble && t.dim() == 2 && t.size(0) == K && t.size(1) == x.size(1) &&
+                    (t.size(1) == 1 || t.stride(1) == 1) && (K == 1 || t.stride(0) >= t.size(1)),
+                "dcfp: `", name, "` must be an fp64 [K, C] tensor with unit column stride");
     return t.data_ptr<double>();
   };
-  d.S1 = arena(S1, "S1", K * x.size(1));
-  d.S2 = arena(S2, "S2", K * x.size(1));
+  d.S1 = arena(S1, "S1");
+  d.S2 = arena(S2, "S2");
+  const int64_t ld1 = K == 1 ? x.size(1) : S1.stride(0), ld2 = K == 1 ? x.size(1) : S2.stride(0);
+  TORCH_CHECK(ld1 == ld2, "dcfp: S1 and S2 must share one row stride");
+  d.ld = static_cast<int32_t>(ld1);
   return d;
 }
 

@@ -66,7 +66,7 @@ int dcfp_label_keys(const void* label, int label_dtype, int N, int H0, int W0, i
  *                           pruners/dcfp_pruner.py:18 reads as m.weight.grad)
  * class key:  keys[n][p] from dcfp_label_keys at this layer's (h, w); key >= K is dropped.
  *             keys == NULL puts every pixel in class 0 (K must be 1).
- * accumulates (+=, fp64):  S1[k*C + c] += sum v,  S2[k*C + c] += sum v*v
+ * accumulates (+=, fp64):  S1[k*ld + c] += sum v,  S2[k*ld + c] += sum v*v
  */
 typedef struct dcfp_layer_desc {
   const void* x;       /* [N,C,h,w] (NCHW) or [N,h,w,C] (NHWC), dtype `dtype` */
@@ -74,13 +74,13 @@ typedef struct dcfp_layer_desc {
   const float* scale;  /* [C] or NULL */
   const float* shift;  /* [C] or NULL */
   const uint8_t* keys; /* [N,h,w] class keys, or NULL */
-  double* S1;          /* [K,C] */
-  double* S2;          /* [K,C] */
+  double* S1;          /* [K, ld] rows; this layer owns columns [0, C) */
+  double* S2;          /* [K, ld] */
   int32_t N, C, h, w;
   int32_t K;
   int32_t dtype;  /* DCFP_F32 | DCFP_BF16 */
   int32_t layout; /* DCFP_NCHW | DCFP_NHWC */
-  int32_t reserved;
+  int32_t ld;     /* row stride of S1/S2 in elements (0 -> C): lets all layers share one [K, sum C] arena */
 } dcfp_layer_desc;
 
 /* ---- K1: label-keyed segmented reduction over conv/BN feature maps -------------------------
@@ -102,7 +102,8 @@ int dcfp_eic_update(const float* const* grad_ptrs, const float* const* gamma_ptr
 /* Same on already-concatenated grad/gamma vectors of n floats. */
 int dcfp_eic_update_flat(const float* grad, const float* gamma, float* eic, int n, float r, float one_minus_r,
                          int first_step, void* stream);
-/* dgamma[c] = sum_k S1[k*C + c]  (fp64 arena -> fp32), the bridge from K1-backward to K2a.     */
+/* dgamma[c] = sum_k S1[k*C + c]  (fp64 arena -> fp32), the bridge from K1-backward to K2a; C may be
+ * the total channel count of a shared [K, sum C] arena (one launch for all layers).             */
 int dcfp_reduce_classes(const double* S1, int K, int C, float* out, void* stream);
 
 /* ---- K2b: global threshold + keep masks -- pruners/dcfp_pruner.py:43-92 ------------------------
