@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- DCFP scoring throughput (images/s) on B200, with the K1 roofline and the CPU reference beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path over one micro-batch (2 images per GPU, fixed by global image index) of
+synthetic Cityscapes-shaped input: forward + backward of the random-init segmentation net (torch / cuDNN produce the
+conv/BN feature maps), the label-keyed segmented reduction K1 over every scored BN layer (hand-written sm_100a kernel,
+deferred into grouped launches), the end-of-step fold, the per-step all-reduce of the BN-gamma gradient (N > 1) and the
+K2 EIC update.  Workload at N = 1: BASELINE.json configs[1] (DeepLabV3-ResNet101, 19 classes, 512x1024).
+
+Printed JSON line (rank 0):
+  value     images/s over all ranks, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the public HOST API dcfp_b200.scorer.score_calibration_set: per step the micro-batch is
+            copied host->device from pinned memory and the loss is read back; scorer set-up and the final score
+            read-back are inside the timed region
+  roofline  K1 only: algorithmic bytes of its launches / their CUDA-event durations inside the timed region,
+            against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's CPU path (oracle/scoring_ref.py) on this box's host cores
+`--impl reference` times that CPU path alone (the reference is pure Python + torch CPU ops; there is no
+compiled reference, so the arm is the oracle port, kind "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dcfp_scoring_images_per_s"
+UNIT = "images/s"
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4"])
+    p.add_argument("--micro-batch", type=int, default=2)
+    p.add_argument("--flush-mb", type=int, default=1024, help="pending feature-map MiB that trigger a grouped K1 launch (0 = per layer)")
+    p.add_argument("--conv-precision", default="fp32", choices=["fp32", "tf32"],
+                   help="cuDNN convolution math of the feature-map producer; fp32 = the reference's precision")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock cap of the reference arm")
+    return p.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.25):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(cfg_name):
+    from dcfp_b200.workloads.segnets import CONFIGS
+    c = dict(CONFIGS[cfg_name])
+    names = {"c1": "DeepLabV3-ResNet50", "c2": "DeepLabV3-ResNet101", "c3": "PSPNet-ResNet101", "c4": "DeepLabV3+-ResNet101"}
+    c["label"] = "%s random-init, %d classes, %dx%d synthetic images (BASELINE.json %s)" % (
+        names[cfg_name], c["num_classes"], c["height"], c["width"], {"c1": "configs[0]", "c2": "configs[1]", "c3": "configs[2]",
+                                                                      "c4": "configs[3]"}[cfg_name])
+    return c
+
+
+def make_batches(c, indices_per_step, pin):
+    from dcfp_b200.workloads.synthetic import synthetic_batch
+    out = []
+    for idx in indices_per_step:
+        x, y = synthetic_batch(idx, c["num_classes"], c["height"], c["width"])
+        out.append((x.pin_memory(), y.pin_memory()) if pin else (x, y))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(c, micro_batch, steps, warmup, budget_s):
+    """The reference's CPU path (restated loop of train.py:255-268 over torch CPU autograd + pruners/dcfp_pruner.py:15-20
+    in oracle/scoring_ref.py), all host threads.  A step = one micro-batch.  Returns (images/s, steps done, s/step)."""
+    import torch
+
+    from dcfp_b200.workloads.segnets import build_segnet
+    from oracle import eic_ref, scoring_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_segnet(c["arch"], c["backbone"], c["num_classes"], seed=0)
+    model.train()
+    layers = scoring_ref.scored_bn_layers(model)
+    eic = {n: 0 for n, _ in layers}
+    batches = make_batches(c, [list(range(i * micro_batch, (i + 1) * micro_batch)) for i in range(2)], pin=False)
+
+    def one(i):
+        x, y = batches[i % len(batches)]
+        torch.manual_seed(i)
+        grads, _ = scoring_ref.gamma_grads(model, x, y)
+        for n, m in layers:
+            eic[n] = eic_ref.eic_step(eic[n], grads[n].numpy(), m.weight.detach().numpy(), 0.999)
+
+    t_begin, per, done_w = time.time(), None, 0
+    for i in range(warmup):  # warm-up may use at most half of the wall-clock budget
+        if per is not None and (time.time() - t_begin) + per > 0.5 * budget_s:
+            break
+        t = time.time()
+        one(i)
+        per = time.time() - t
+        done_w += 1
+    done, t0 = 0, time.time()
+    while done < steps:  # the timed steps stop early (and say so) rather than overrun the budget
+        if per is not None and done >= 1 and (time.time() - t_begin) + per > budget_s:
+            break
+        t = time.time()
+        one(done_w + done)
+        per = time.time() - t
+        done += 1
+    dt = time.time() - t0
+    return done * micro_batch / dt, done, dt / done, cores, done_w
+
+
+def run_reference_arm(args, c):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, done, s_per, cores, done_w = cpu_reference(c, args.micro_batch, args.steps, args.warmup, args.cpu_budget_s)
+    sample = "%d timed micro-batches of %d images (%d warm-up) of the %s workload, fp32, %d host threads" % (
+        done, args.micro_batch, done_w, args.config, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": done_w, "ms_per_step": s_per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c["label"], "micro_batch": args.micro_batch, "protocol": "zero_grad -> loss(x, y, deepsup) -> "
+                       "backward -> dcfp_pruning.step, no optimizer step", "requested_steps": args.steps,
+                       "requested_warmup": args.warmup},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200_arm(args, c):
+    import torch
+    import torch.distributed as dist
+
+    from dcfp_b200 import ops
+    from dcfp_b200.scorer import CalibrationRun, score_calibration_set
+    from dcfp_b200.workloads.segnets import build_segnet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nproc-per-node %d bench.py ..." % (args.gpus, args.gpus))
+    ops.require_gpu()  # no CPU fallback: fail loudly
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    tf32 = args.conv_precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = True
+
+    K, W, mb = args.steps, args.warmup, args.micro_batch
+    model = build_segnet(c["arch"], c["backbone"], c["num_classes"], seed=0).to(dev)
+    n_steps_total = W + K
+    # global micro-batch index of (step s, rank r) = s * world + r  -- the plan of scorer.shard_plan
+    idx = [list(range((s * world + rank) * mb, (s * world + rank + 1) * mb)) for s in range(n_steps_total)]
+    host = make_batches(c, idx, pin=True)
+    resident = [(x.to(dev), y.to(dev)) for x, y in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- phase A: inputs resident in HBM -------------------------------------------------------------------
+    run = CalibrationRun(model, c["num_classes"], r=0.999, flush_bytes=args.flush_mb << 20, keep_totals=True, timing=True, seed=0)
+    sc = run.scorer
+    for s in range(W):
+        run.step(*resident[s], mb_index=s * world + rank)
+    barrier()
+    sc.k1_events.clear()
+    launches0 = ops.launch_count()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    barrier()
+    e0.record()
+    for s in range(W, W + K):
+        run.step(*resident[s], mb_index=s * world + rank)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_a = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count() - launches0
+    k1_ms, k1_bytes, k1_launches = sc.k1_time_ms()
+    share_a = k1_ms / max(e0.elapsed_time(e1), 1e-9)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    sc.all_reduce_totals()  # the single end-of-pass statistics all-reduce (outside the per-step timing, reported below)
+    if world > 1:
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        sc.all_reduce_totals()
+        eb.record()
+        torch.cuda.synchronize()
+        allreduce_ms = max_over_ranks(ea.elapsed_time(eb))
+    else:
+        allreduce_ms = 0.0
+    arena_bytes = sc.total_arena.numel() * 8
+    sum_c = sc.total_channels
+    run.close()
+    del run, sc, resident
+    torch.cuda.empty_cache()
+    value = K * mb * world / (ms_a * 1e-3)
+
+    # ---- phase B: public host API, H2D + D2H inside the timed region -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        # score_calibration_set shards by rank itself (shard_plan): hand it the images in GLOBAL order.  This rank
+        # only ever reads its own slices, so the other ranks' slots repeat its own micro-batch as placeholders.
+        def global_order(lo, hi):
+            xs = [host[s][0] for s in range(lo, hi) for _ in range(world)]
+            ys = [host[s][1] for s in range(lo, hi) for _ in range(world)]
+            return torch.cat(xs).pin_memory(), torch.cat(ys).pin_memory()
+        if W:
+            xw, yw = global_order(0, W)
+            score_calibration_set(model, xw, yw, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20)
+        xk, yk = global_order(W, W + K)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = score_calibration_set(model, xk, yk, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20)
+        e1.record()
+        barrier()
+        ms_b = max_over_ranks(e0.elapsed_time(e1))
+        st = out["_stats"]
+        assert st["steps"] == K
+        e2e = {"value": K * mb * world / (ms_b * 1e-3), "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] // K,
+               "d2h_bytes_per_step": st["d2h_bytes"] / K, "ms_per_step": ms_b / K,
+               "api": "dcfp_b200.scorer.score_calibration_set(model, host_images, host_labels, K)"}
+
+    peak, peak_src = hbm_peak()
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    roofline = {"kernel": "dcfp::class_stats_kernel<float, BWD> (K1, label-keyed segmented reduction, v = dy * xhat)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "traffic_note": traffic.get("note") if traffic else "no ncu --set full capture recorded yet",
+                "launches": k1_launches, "algorithmic_bytes_per_launch": k1_bytes / max(k1_launches, 1),
+                "avg_launch_ms": k1_ms / max(k1_launches, 1), "share_of_step": share_a,
+                "algorithmic_bytes_per_image": k1_bytes / (K * mb)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, done, s_per, cores, done_w = cpu_reference(c, mb, 1, 0, 120.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 micro-batch of %d images of the same workload (%.1f s), fp32, oracle/scoring_ref.py, no warm-up" % (mb, s_per)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_a / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": c["label"], "micro_batch_per_gpu": mb, "calibration_images_nominal": 500,
+                           "images_timed": K * mb * world, "sum_scored_channels": sum_c, "conv_math": args.conv_precision,
+                           "protocol": "zero_grad -> loss(x, y, deepsup) -> backward [K1 on every scored BN: S[k,c] += dy*xhat] -> "
+                                       "fold -> all-reduce(dgamma)/N -> EIC update; no optimizer step",
+                           "l2": "per-step feature maps (%.1f GB read by K1) exceed the 126 MB L2; no explicit flush" % (k1_bytes / K / 1e9),
+                           "k1_flush_mib": args.flush_mb, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K,sumC] fp64 totals + counts at the end of the pass"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    c = workload(args.config)
+    if args.impl == "reference":
+        run_reference_arm(args, c)
+    else:
+        run_b200_arm(args, c)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,8 @@ class LayerDesc(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("dy", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
                 ("keys", ctypes.c_void_p), ("S1", ctypes.c_void_p), ("S2", ctypes.c_void_p),
                 ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
-                ("K", ctypes.c_int32), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32), ("ld", ctypes.c_int32)]
+                ("K", ctypes.c_int32), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32), ("ld", ctypes.c_int32),
+                ("affine_mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class GatherDesc(ctypes.Structure):
@@ -58,6 +59,7 @@ def load(path=LIB_PATH):
     lib.dcfp_eic_update.argtypes = [vp, vp, vp, i32, vp, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_eic_update_flat.argtypes = [vp, vp, vp, i32, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_reduce_classes.argtypes = [vp, i32, i32, vp, vp]
+    lib.dcfp_fold_step.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.dcfp_thresh_mask.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.POINTER(i64), vp, vp, vp, vp]
     lib.dcfp_channel_gather.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]
     lib.dcfp_channel_gather_workspace.restype = ctypes.c_size_t

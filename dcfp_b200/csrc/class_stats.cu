@@ -54,6 +54,7 @@ struct LayerDev {
   double* S2;
   int32_t C, HW, n_cg, ld;
   int32_t boxes_per_plane, n_boxes, boxes_per_chunk;
+  int32_t centered;  // DCFP_AFFINE_INVSTD_MEAN: shift holds the batch mean
 };
 
 // Layer table + TMA descriptors in kernel parameter space (no H2D copy, no workspace).
@@ -263,6 +264,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   if (lane < n_active) {
     if (L.scale) sc = L.scale[row0 + lane];
     if (L.shift) sf = L.shift[row0 + lane];
+    if (L.centered) sf = -sf * sc;  // (x - mean) * invstd == x * invstd + (-mean * invstd)
   }
   const f2 sc2 = pack2(sc, sc), sf2 = pack2(sf, sf);
 
@@ -388,7 +390,7 @@ struct GenericLayer {
   const float* shift;
   double* S1;
   double* S2;
-  int32_t C, HW, ld;
+  int32_t C, HW, ld, centered;
 };
 template <typename T, bool BWD>
 __global__ void class_stats_generic_kernel(const GenericLayer L, const int K, const int nhwc, const int px_per_block) {
@@ -396,7 +398,9 @@ __global__ void class_stats_generic_kernel(const GenericLayer L, const int K, co
   const int n = blockIdx.z;
   const int p_begin = blockIdx.y * px_per_block, p_end = min(p_begin + px_per_block, L.HW);
   if (c >= L.C) return;
-  const float sc = L.scale ? L.scale[c] : 1.f, sf = L.shift ? L.shift[c] : 0.f;
+  const float sc = L.scale ? L.scale[c] : 1.f;
+  float sf = L.shift ? L.shift[c] : 0.f;
+  if (L.centered) sf = -sf * sc;
   const T* x = reinterpret_cast<const T*>(L.x);
   const T* dy = reinterpret_cast<const T*>(L.dy);
   float a1 = 0.f, a2 = 0.f;
@@ -505,6 +509,11 @@ int validate(const dcfp_layer_desc& d, int idx) {
   DCFP_REQUIRE(d.dtype == DCFP_F32 || d.dtype == DCFP_BF16, DCFP_EINVAL, "class_stats[%d]: unknown dtype %d", idx, d.dtype);
   DCFP_REQUIRE(d.layout == DCFP_NCHW || d.layout == DCFP_NHWC, DCFP_EINVAL, "class_stats[%d]: unknown layout %d", idx, d.layout);
   DCFP_REQUIRE(d.ld == 0 || d.ld >= d.C, DCFP_EINVAL, "class_stats[%d]: ld=%d < C=%d", idx, d.ld, d.C);
+  DCFP_REQUIRE(d.affine_mode == DCFP_AFFINE_SCALE_SHIFT || d.affine_mode == DCFP_AFFINE_INVSTD_MEAN, DCFP_EINVAL,
+               "class_stats[%d]: unknown affine_mode %d", idx, d.affine_mode);
+  DCFP_REQUIRE(d.affine_mode == DCFP_AFFINE_SCALE_SHIFT || (d.scale && d.shift), DCFP_EINVAL,
+               "class_stats[%d]: DCFP_AFFINE_INVSTD_MEAN needs both scale (invstd) and shift (mean)", idx);
+  DCFP_REQUIRE(d.reserved == 0, DCFP_EINVAL, "class_stats[%d]: reserved field must be 0", idx);
   DCFP_REQUIRE(d.keys != nullptr || d.K == 1, DCFP_EINVAL, "class_stats[%d]: keys == NULL requires K == 1", idx);
   DCFP_REQUIRE(static_cast<long long>(d.h) * d.w < (1LL << 30), DCFP_ETOOBIG, "class_stats[%d]: plane too large", idx);
   DCFP_REQUIRE(static_cast<long long>(d.N) * d.C < (1LL << 31), DCFP_ETOOBIG, "class_stats[%d]: too many planes", idx);
@@ -525,7 +534,8 @@ bool tiled_ok(const dcfp_layer_desc& d) {
 
 template <typename T, bool BWD>
 int launch_generic(const dcfp_layer_desc& d, cudaStream_t stream) {
-  GenericLayer L{d.x, d.dy, d.keys, d.scale, d.shift, d.S1, d.S2, d.C, d.h * d.w, d.ld > 0 ? d.ld : d.C};
+  GenericLayer L{d.x, d.dy, d.keys, d.scale, d.shift, d.S1, d.S2, d.C, d.h * d.w, d.ld > 0 ? d.ld : d.C,
+                 d.affine_mode == DCFP_AFFINE_INVSTD_MEAN};
   const int threads = 128;
   const int px_per_block = 256;
   dim3 grid((d.C + threads - 1) / threads, (L.HW + px_per_block - 1) / px_per_block, d.N);
@@ -574,6 +584,7 @@ int run_tiled(const dcfp_layer_desc* descs, const int* which, int n, int boxes_p
     L.S2 = d.S2;
     L.C = d.C;
     L.ld = d.ld > 0 ? d.ld : d.C;
+    L.centered = d.affine_mode == DCFP_AFFINE_INVSTD_MEAN;
     L.HW = d.h * d.w;
     L.n_cg = (d.C + 31) / 32;
     L.boxes_per_plane = (L.HW + kBoxPx - 1) / kBoxPx;

@@ -54,6 +54,26 @@ __global__ void reduce_classes_kernel(const double* __restrict__ S1, int K, int 
   out[c] = static_cast<float>(s);
 }
 
+// end-of-step fold: dgamma = sum_k step.S1, total += step, step = 0  (one coalesced pass, thread == channel)
+__global__ void fold_step_kernel(double* __restrict__ step, double* __restrict__ total, int K, int C, float* __restrict__ dgamma) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const size_t plane = static_cast<size_t>(K) * C;
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const size_t o = static_cast<size_t>(k) * C + c;
+    const double a = step[o], b = step[plane + o];
+    s += a;
+    if (total != nullptr) {
+      if (a != 0.0) total[o] += a;
+      if (b != 0.0) total[plane + o] += b;
+    }
+    if (a != 0.0) step[o] = 0.0;
+    if (b != 0.0) step[plane + o] = 0.0;
+  }
+  if (dgamma != nullptr) dgamma[c] = static_cast<float>(s);
+}
+
 // ---- K2b -------------------------------------------------------------------------------------
 // order-preserving float -> uint key (ascending); +NaN sorts last like torch.sort
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -207,6 +227,13 @@ extern "C" int dcfp_reduce_classes(const double* S1, int K, int C, float* out, v
   DCFP_REQUIRE(K > 0 && C > 0, DCFP_EINVAL, "reduce_classes: K=%d C=%d", K, C);
   reduce_classes_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(S1, K, C, out);
   return finish_launch("reduce_classes");
+}
+
+extern "C" int dcfp_fold_step(double* step, double* total, int K, int C, float* dgamma, void* stream) {
+  DCFP_REQUIRE(step != nullptr, DCFP_EINVAL, "fold_step: null step arena");
+  DCFP_REQUIRE(K > 0 && C > 0, DCFP_EINVAL, "fold_step: K=%d C=%d", K, C);
+  fold_step_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(step, total, K, C, dgamma);
+  return finish_launch("fold_step");
 }
 
 extern "C" int dcfp_thresh_mask(const float* score, const int32_t* layer_off, const int32_t* layer_group, const int32_t* min_keep,

@@ -40,7 +40,7 @@ int label_dtype_of(const Tensor& label) {
 // Fills one descriptor; keeps nothing alive (the caller holds the tensors).
 dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const optional<Tensor>& scale,
                           const optional<Tensor>& shift, const optional<Tensor>& keys, const Tensor& S1, const Tensor& S2,
-                          int64_t K) {
+                          int64_t K, int64_t affine_mode) {
   require_cuda(x, "x");
   TORCH_CHECK(x.dim() == 4, "dcfp: feature map must be 4-D [N,C,h,w], got ", x.dim(), "-D");
   TORCH_CHECK(x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16, "dcfp: feature map must be fp32 or bf16");
@@ -56,6 +56,7 @@ dcfp_layer_desc make_desc(const Tensor& x, const optional<Tensor>& dy, const opt
   d.h = static_cast<int32_t>(x.size(2));
   d.w = static_cast<int32_t>(x.size(3));
   d.K = static_cast<int32_t>(K);
+  d.affine_mode = static_cast<int32_t>(affine_mode);
   if (dy.has_value()) {
     const Tensor& g = *dy;
     require_cuda(g, "dy");
@@ -117,15 +118,15 @@ Tensor label_keys(const Tensor& label, int64_t h, int64_t w, int64_t K, optional
 }
 
 void class_stats(const Tensor& x, const optional<Tensor>& dy, const optional<Tensor>& scale, const optional<Tensor>& shift,
-                 const optional<Tensor>& keys, Tensor S1, Tensor S2, int64_t K) {
-  const dcfp_layer_desc d = make_desc(x, dy, scale, shift, keys, S1, S2, K);
+                 const optional<Tensor>& keys, Tensor S1, Tensor S2, int64_t K, int64_t affine_mode) {
+  const dcfp_layer_desc d = make_desc(x, dy, scale, shift, keys, S1, S2, K, affine_mode);
   c10::cuda::CUDAGuard guard(x.device());
   check_rc(dcfp_class_stats(&d, cur_stream()), "class_stats");
 }
 
 // keys: one tensor per layer (layers of equal resolution pass the same tensor), or empty when K == 1
 void class_stats_grouped(at::TensorList xs, at::TensorList dys, at::TensorList scales, at::TensorList shifts,
-                         at::TensorList keys, at::TensorList S1s, at::TensorList S2s, int64_t K) {
+                         at::TensorList keys, at::TensorList S1s, at::TensorList S2s, int64_t K, int64_t affine_mode) {
   const size_t n = xs.size();
   TORCH_CHECK(n > 0, "dcfp::class_stats_grouped: empty layer list");
   TORCH_CHECK(S1s.size() == n && S2s.size() == n, "dcfp::class_stats_grouped: S1/S2 lists must match xs");
@@ -139,7 +140,7 @@ void class_stats_grouped(at::TensorList xs, at::TensorList dys, at::TensorList s
     optional<Tensor> sc = scales.empty() ? optional<Tensor>() : optional<Tensor>(scales[i]);
     optional<Tensor> sf = shifts.empty() ? optional<Tensor>() : optional<Tensor>(shifts[i]);
     optional<Tensor> ky = keys.empty() ? optional<Tensor>() : optional<Tensor>(keys[i]);
-    descs[i] = make_desc(xs[i], dy, sc, sf, ky, S1s[i], S2s[i], K);
+    descs[i] = make_desc(xs[i], dy, sc, sf, ky, S1s[i], S2s[i], K, affine_mode);
   }
   c10::cuda::CUDAGuard guard(xs[0].device());
   for (size_t first = 0; first < n; first += DCFP_MAX_GROUP_LAYERS) {
@@ -156,6 +157,26 @@ Tensor reduce_classes(const Tensor& S1) {
   check_rc(dcfp_reduce_classes(S1.data_ptr<double>(), static_cast<int>(S1.size(0)), static_cast<int>(S1.size(1)),
                                out.data_ptr<float>(), cur_stream()),
            "reduce_classes");
+  return out;
+}
+
+// step / total: fp64 [2, K, C]; returns dgamma fp32 [C]
+Tensor fold_step(Tensor step, const optional<Tensor>& total) {
+  require_cuda(step, "step");
+  TORCH_CHECK(step.scalar_type() == at::kDouble && step.is_contiguous() && step.dim() == 3 && step.size(0) == 2,
+              "dcfp::fold_step: step must be a contiguous fp64 [2,K,C] arena");
+  double* tp = nullptr;
+  if (total.has_value()) {
+    require_cuda(*total, "total");
+    TORCH_CHECK(total->scalar_type() == at::kDouble && total->is_contiguous() && total->sizes() == step.sizes(),
+                "dcfp::fold_step: total must match step");
+    tp = total->data_ptr<double>();
+  }
+  Tensor out = at::empty({step.size(2)}, step.options().dtype(at::kFloat));
+  c10::cuda::CUDAGuard guard(step.device());
+  check_rc(dcfp_fold_step(step.data_ptr<double>(), tp, static_cast<int>(step.size(1)), static_cast<int>(step.size(2)),
+                          out.data_ptr<float>(), cur_stream()),
+           "fold_step");
   return out;
 }
 
@@ -326,13 +347,14 @@ int64_t abi_version() { return dcfp_abi_version(); }
 
 TORCH_LIBRARY(dcfp, m) {
   m.def("label_keys(Tensor label, int h, int w, int K, Tensor(a!)? cnt) -> Tensor", &label_keys);
-  m.def("class_stats(Tensor x, Tensor? dy, Tensor? scale, Tensor? shift, Tensor? keys, Tensor(a!) S1, Tensor(b!) S2, int K) -> ()",
+  m.def("class_stats(Tensor x, Tensor? dy, Tensor? scale, Tensor? shift, Tensor? keys, Tensor(a!) S1, Tensor(b!) S2, int K, int affine_mode=0) -> ()",
         &class_stats);
   m.def(
       "class_stats_grouped(Tensor[] xs, Tensor[] dys, Tensor[] scales, Tensor[] shifts, Tensor[] keys, Tensor(a!)[] S1s, "
-      "Tensor(b!)[] S2s, int K) -> ()",
+      "Tensor(b!)[] S2s, int K, int affine_mode=0) -> ()",
       &class_stats_grouped);
   m.def("reduce_classes(Tensor S1) -> Tensor", &reduce_classes);
+  m.def("fold_step(Tensor(a!) step, Tensor(b!)? total) -> Tensor", &fold_step);
   m.def("eic_update(Tensor[] grads, Tensor[] gammas, Tensor offsets, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",
         &eic_update);
   m.def("eic_update_flat(Tensor grad, Tensor gamma, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",

@@ -53,15 +53,24 @@ def label_keys(label, h, w, K, cnt=None):
     return load().label_keys(label, int(h), int(w), int(K), cnt)
 
 
-def class_stats(x, keys, K, S1, S2, dy=None, scale=None, shift=None):
-    """S1[k,c] += sum v, S2[k,c] += sum v*v over the pixels whose class key is k (keys from label_keys)."""
-    load().class_stats(x, dy, scale, shift, keys, S1, S2, int(K))
+AFFINE_SCALE_SHIFT, AFFINE_INVSTD_MEAN = 0, 1
 
 
-def class_stats_grouped(xs, keys, K, S1s, S2s, dys=None, scales=None, shifts=None):
+def class_stats(x, keys, K, S1, S2, dy=None, scale=None, shift=None, affine_mode=AFFINE_SCALE_SHIFT):
+    """S1[k,c] += sum v, S2[k,c] += sum v*v over the pixels whose class key is k (keys from label_keys).
+    affine_mode=AFFINE_INVSTD_MEAN: scale = invstd, shift = batch mean (what autograd's BN node saved)."""
+    load().class_stats(x, dy, scale, shift, keys, S1, S2, int(K), int(affine_mode))
+
+
+def class_stats_grouped(xs, keys, K, S1s, S2s, dys=None, scales=None, shifts=None, affine_mode=AFFINE_SCALE_SHIFT):
     """One launch over many resident feature maps (same dtype / K / functor); keys: one tensor per layer."""
     load().class_stats_grouped(list(xs), list(dys or []), list(scales or []), list(shifts or []), list(keys or []), list(S1s),
-                               list(S2s), int(K))
+                               list(S2s), int(K), int(affine_mode))
+
+
+def fold_step(step, total=None):
+    """dgamma[c] = sum_k step[0,k,c]; total += step; step = 0 -- one launch.  step/total: fp64 [2,K,C]."""
+    return load().fold_step(step, total)
 
 
 def reduce_classes(S1):

@@ -11,8 +11,15 @@ class of each pixel (north_star "class-conditional calibration statistics"):
   mode "bwd":  v = dy * xhat   -> sum_k S1[k, c] == bn.weight.grad  (reference-exact EIC feed)
   mode "fwd":  v = BN output y -> class-conditional mean / variance of the feature map
 
-All layers write into ONE fp64 arena [S1 (K x sumC) | S2 (K x sumC) | cnt (R x K)] so that the
-multi-GPU combine is a single all-reduce and the class reduction / EIC update are one launch each.
+HBM layout: all layers write into ONE fp64 *step arena* [2, K, sumC] (S1 rows,
+then S2 rows; layer l owns columns [off_l, off_l + C_l)), so that
+  * the end-of-step fold (dgamma = sum_k S1, totals += step, step = 0) is one launch,
+  * the multi-GPU combine is one all-reduce of the *total arena* [2, K, sumC] + cnt [R, K].
+Backward-mode launches are DEFERRED: the hook only records (x, dy, mean, invstd) -- tensors autograd
+holds anyway, or that live for microseconds otherwise -- and `flush()` reduces every pending layer
+in ONE grouped K1 launch once `flush_bytes` of feature maps are pending (180 GB of HBM make holding a
+few GB of gradients free; a grouped launch runs at ~93 % of the HBM roofline, a 16 MB single-layer
+launch at ~25-45 %).
 """
 import torch
 import torch.nn as nn
@@ -28,8 +35,32 @@ def scored_layers(model):
     return [(n, m) for n, m in model.named_modules() if isinstance(m, (nn.BatchNorm2d, nn.SyncBatchNorm)) and n not in ignore]
 
 
+def shard_plan(n_images, micro_batch, world, rank):
+    """Image indices rank `rank` scores at each step: micro-batches are fixed by GLOBAL image index
+    ([0,mb), [mb,2mb), ...) and dealt round-robin, so the set of micro-batches -- and therefore every
+    BN batch statistic -- does not depend on the number of GPUs.  Returns a list over steps of
+    (lo, hi) slices; a trailing remainder that cannot fill `world` micro-batches is dropped."""
+    if micro_batch < 1 or world < 1 or not 0 <= rank < world:
+        raise ValueError("bad shard plan arguments")
+    n_steps = n_images // (micro_batch * world)
+    return [((s * world + rank) * micro_batch, (s * world + rank + 1) * micro_batch) for s in range(n_steps)]
+
+
+def average_over_ranks(t, group=None):
+    """In-place mean over ranks of a small per-step vector (the reference's DDP averages gradients before
+    `dcfp_pruning.step` sees them, engine.py:66).  One all-reduce; no-op without torch.distributed."""
+    dist = torch.distributed
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(t, group=group)
+            t /= world
+    return t
+
+
 class ClassStatsScorer:
-    def __init__(self, model, num_classes, mode="bwd", r=0.999, process_group=None):
+    def __init__(self, model, num_classes, mode="bwd", r=0.999, process_group=None, flush_bytes=1 << 30, keep_totals=True,
+                 timing=False):
         ops.require_gpu()
         assert mode in ("bwd", "fwd")
         self.model, self.K, self.mode, self.r = model, int(num_classes), mode, r
@@ -47,18 +78,27 @@ class ClassStatsScorer:
             self.offsets.append(self.offsets[-1] + s)
         self.total_channels = self.offsets[-1]
         K, C = self.K, self.total_channels
-        self.arena = torch.zeros(2 * K * C + MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device)
-        self.S1 = self.arena[:K * C].view(K, C)
-        self.S2 = self.arena[K * C:2 * K * C].view(K, C)
-        self.cnt = self.arena[2 * K * C:].view(MAX_RESOLUTIONS, K)
-        self._views = {n: (self.S1[:, a:b], self.S2[:, a:b]) for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
+        self.step_arena = torch.zeros(2, K, C, dtype=torch.float64, device=self.device)
+        # pass-wide totals and pixel counts share one buffer: ONE all-reduce combines everything
+        self.total_arena = torch.zeros(2 * K * C + MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device) if keep_totals else None
+        self.totals = self.total_arena[:2 * K * C].view(2, K, C) if keep_totals else None
+        self.cnt = (self.total_arena[2 * K * C:] if keep_totals else
+                    torch.zeros(MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device)).view(MAX_RESOLUTIONS, K)
+        self._views = {n: (self.step_arena[0][:, a:b], self.step_arena[1][:, a:b])
+                       for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
         self.resolutions = []  # (h, w) in discovery order -> row of `cnt`
         self._keys = {}
         self._labels = None
         self._handles = []
+        self.flush_bytes = int(flush_bytes)
+        self._pending = []
+        self._pending_bytes = 0
         self.eic = torch.zeros(C, dtype=torch.float32, device=self.device)
+        self._gamma = None
         self.steps = 0
-        self.launches = 0
+        self.timing = timing
+        self.k1_events = []  # (start, end, algorithmic bytes) per K1 launch when timing
+        self.k1_bytes = 0
 
     # ------------------------------------------------------------------ hooks
     def attach(self):
@@ -70,6 +110,7 @@ class ClassStatsScorer:
         for h in self._handles:
             h.remove()
         self._handles = []
+        self._pending, self._pending_bytes = [], 0
 
     def set_labels(self, labels):
         """labels of the micro-batch about to run: [N, H0, W0] uint8 / int32 / int64 on the device."""
@@ -85,8 +126,40 @@ class ClassStatsScorer:
                 self.resolutions.append(key)
             row = self.cnt[self.resolutions.index(key)]
             self._keys[key] = ops.label_keys(self._labels, h, w, self.K, row)
-            self.launches += 1
         return self._keys[key]
+
+    @staticmethod
+    def _dense(t):
+        return t if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last) else t.contiguous()
+
+    def _launch(self, items):
+        """ONE K1 launch over `items` = [(x, dy|None, scale|None, shift|None, keys, S1, S2)], optionally timed."""
+        nbytes = sum(x.numel() * x.element_size() * (2 if dy is not None else 1) + k.numel() for x, dy, _, _, k, _, _ in items)
+        if self.timing:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        bwd = items[0][1] is not None
+        ops.class_stats_grouped([i[0] for i in items], [i[4] for i in items], self.K, [i[5] for i in items], [i[6] for i in items],
+                                dys=[i[1] for i in items] if bwd else None,
+                                scales=[i[2] for i in items] if bwd else None, shifts=[i[3] for i in items] if bwd else None,
+                                affine_mode=ops.AFFINE_INVSTD_MEAN if bwd else ops.AFFINE_SCALE_SHIFT)
+        if self.timing:
+            e1.record()
+            self.k1_events.append((e0, e1, nbytes))
+        self.k1_bytes += nbytes
+
+    def flush(self):
+        """Reduce every pending (deferred) backward-mode layer; grouped by (dtype, layout) as one launch needs."""
+        if not self._pending:
+            return
+        groups = {}
+        for item in self._pending:
+            x = item[0]
+            groups.setdefault((x.dtype, x.is_contiguous()), []).append(item)
+        self._pending, self._pending_bytes = [], 0
+        for items in groups.values():
+            self._launch(items)
 
     def _make_hook(self, name):
         S1, S2 = self._views[name]
@@ -96,10 +169,8 @@ class ClassStatsScorer:
                 return
             x = inputs[0]
             if self.mode == "fwd":
-                y = output.detach()
-                y = y if y.is_contiguous() or y.is_contiguous(memory_format=torch.channels_last) else y.contiguous()
-                ops.class_stats(y, self._keys_for(y.shape[2], y.shape[3]), self.K, S1, S2)
-                self.launches += 1
+                y = self._dense(output.detach())
+                self._launch([(y, None, None, None, self._keys_for(y.shape[2], y.shape[3]), S1, S2)])
                 return
             if not output.requires_grad:
                 return
@@ -108,117 +179,174 @@ class ClassStatsScorer:
 
             def on_grad(dy):
                 with torch.no_grad():
-                    mean = getattr(node, "_saved_result1", None) if training else None
-                    invstd = getattr(node, "_saved_result2", None) if training else None
                     xd = x.detach()
-                    if not training:
-                        mean = module.running_mean
-                        invstd = torch.rsqrt(module.running_var + module.eps)
-                    elif mean is None or invstd is None or mean.numel() != xd.shape[1]:
-                        var, mean = torch.var_mean(xd.float(), dim=(0, 2, 3), unbiased=False)
-                        invstd = torch.rsqrt(var + module.eps)
-                    scale = invstd.float().contiguous()
-                    shift = (-mean.float() * scale).contiguous()
-                    g = dy if dy.is_contiguous() or dy.is_contiguous(memory_format=torch.channels_last) else dy.contiguous()
+                    if training:
+                        mean = getattr(node, "_saved_result1", None)
+                        invstd = getattr(node, "_saved_result2", None)
+                        if mean is None or invstd is None or mean.numel() != xd.shape[1] or mean.dtype != torch.float32:
+                            # BN implementation that saves nothing usable: recompute the batch statistics
+                            var, mean = torch.var_mean(xd.float(), dim=(0, 2, 3), unbiased=False)
+                            invstd = torch.rsqrt(var + module.eps)
+                    else:
+                        mean = module.running_mean.float()
+                        invstd = torch.rsqrt(module.running_var.float() + module.eps)
+                    g = self._dense(dy)
                     if xd.stride() != g.stride():
                         xd, g = xd.contiguous(), g.contiguous()
-                    ops.class_stats(xd, self._keys_for(xd.shape[2], xd.shape[3]), self.K, S1, S2, dy=g, scale=scale, shift=shift)
-                    self.launches += 1
+                    item = (xd, g, invstd.contiguous(), mean.contiguous(), self._keys_for(xd.shape[2], xd.shape[3]), S1, S2)
+                    if self.flush_bytes <= 0:
+                        self._launch([item])
+                        return
+                    self._pending.append(item)
+                    self._pending_bytes += 2 * xd.numel() * xd.element_size()
+                    if self._pending_bytes >= self.flush_bytes:
+                        self.flush()
 
             output.register_hook(on_grad)
 
         return hook
 
     # ------------------------------------------------------------------ reductions
-    def zero_stats(self):
-        self.arena.zero_()
+    def fold_step(self):
+        """End of one step: flush deferred layers, then ONE launch yields dgamma = sum_k S1 (fp32 [sumC]),
+        adds the step arena into the pass totals and zeroes it for the next step."""
+        self.flush()
+        return ops.fold_step(self.step_arena, self.totals)
 
-    def all_reduce(self):
-        """ONE collective for all layers, classes and counts (SUM, fp64, NCCL over NVLink)."""
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            if torch.distributed.get_world_size(self.group) > 1:
-                torch.distributed.all_reduce(self.arena, group=self.group)
+    def all_reduce_totals(self):
+        """ONE collective for all layers, both moments and the pixel counts (SUM, fp64, NCCL over NVLink)."""
+        dist = torch.distributed
+        if self.total_arena is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.total_arena, group=self.group)
 
-    def dgamma(self):
-        """sum_k S1[k, c] for every scored channel, fp32 [sumC] -- ONE launch over the shared arena."""
-        self.launches += 1
-        return ops.reduce_classes(self.S1)
+    def gamma(self):
+        if self._gamma is None:
+            self._gamma = torch.cat([m.weight.detach().reshape(-1) for _, m in self.layers]).float()
+        return self._gamma
 
-    def eic_step(self, dgamma=None, gamma=None):
-        """One EIC update (dcfp_pruner.py:15-20) from the class-resolved BN-gamma gradient."""
-        dgamma = self.dgamma() if dgamma is None else dgamma
-        if gamma is None:
-            gamma = torch.cat([m.weight.detach().reshape(-1) for _, m in self.layers]).float()
-        ops.eic_update_flat(dgamma, gamma, self.eic, self.r, first_step=(self.steps == 0))
-        self.launches += 1
+    def eic_step(self, dgamma):
+        """One EIC update (dcfp_pruner.py:15-20) from the (rank-averaged) BN-gamma gradient of this step."""
+        ops.eic_update_flat(dgamma, self.gamma(), self.eic, self.r, first_step=(self.steps == 0))
         self.steps += 1
-        return dgamma
 
     def eic_dict(self):
         """`{'eic': {bn_name: Tensor[C]}}` -- the layout of score.pth (dcfp_pruner.py:10,25-26)."""
         return {"eic": {n: self.eic[a:b].clone() for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}}
 
     def class_stats(self):
-        """{name: (S1[K,C], S2[K,C])} views plus per-resolution counts."""
-        return dict(self._views), {r: self.cnt[i] for i, r in enumerate(self.resolutions)}
+        """Pass totals {name: (S1[K,C], S2[K,C])} plus per-resolution pixel counts {(h,w): cnt[K]}."""
+        src = self.totals if self.totals is not None else self.step_arena
+        views = {n: (src[0][:, a:b], src[1][:, a:b]) for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
+        return views, {r: self.cnt[i] for i, r in enumerate(self.resolutions)}
+
+    def k1_time_ms(self):
+        """(sum of K1 launch durations in ms, algorithmic bytes, launches) -- call after a synchronize."""
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.k1_events)
+        return ms, sum(b for _, _, b in self.k1_events), len(self.k1_events)
 
 
-def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, pin=True):
-    """Public end-to-end call: HOST images/labels -> EIC scores on the host.
+class CalibrationRun:
+    """Step-wise driver of the scoring pass (bench.py times `step`; `score_calibration_set` loops it).
 
-    Protocol (the oracle follows the same one): for every micro-batch of
-    `micro_batch` images (fixed by global index)  zero_grad -> loss = model(x, y, deepsup=True)
-    -> backward -> one EIC step on the gradient of this step; BN runs in train mode on the
-    micro-batch like the reference's training step (train.py:255-268), no optimizer step, running
-    statistics restored afterwards.  With torch.distributed initialised, micro-batches are dealt
-    round-robin to the ranks and each step's dgamma vector is averaged with one all-reduce before
-    the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
+    Protocol (oracle/scoring_ref.py follows the same one): for every micro-batch
+    (fixed by global image index)  zero_grad -> loss = model(x, y, deepsup=True) -> backward -> EIC step
+    on this step's gradient; BN runs in train mode on the micro-batch like the reference's training
+    step (train.py:255-268), no optimizer step, running statistics restored at `close`.  With
+    torch.distributed initialised every step's dgamma vector is averaged over the ranks with one
+    all-reduce before the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
+
+    def __init__(self, model, num_classes, r=0.999, mode="bwd", restore_bn_stats=True, flush_bytes=1 << 30, keep_totals=True,
+                 timing=False, process_group=None, seed=None):
+        ops.require_gpu()
+        self.model = model
+        self.seed = seed
+        self.device = next(model.parameters()).device
+        self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
+                                       keep_totals=keep_totals, timing=timing).attach()
+        self._saved = None
+        if restore_bn_stats:
+            self._saved = [(m, m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone())
+                           for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.running_mean is not None]
+        self._was_training = model.training
+        model.train()
+        self.group = process_group
+        self.closed = False
+
+    def step(self, x, y, mb_index=None):
+        """x [N,3,H,W] fp32, y [N,H,W] integer labels, both ON THE DEVICE.  Returns the loss tensor (device).
+        mb_index: GLOBAL micro-batch index; with `seed` set the RNG (Dropout2d of the deep-supervision head,
+        deeplabv3.py:40) is keyed by it so that results do not depend on the number of ranks."""
+        sc = self.scorer
+        if self.seed is not None and mb_index is not None:
+            torch.manual_seed(self.seed + int(mb_index))
+        sc.set_labels(y)
+        self.model.zero_grad(set_to_none=True)
+        out = self.model(x, y if y.dtype == torch.long else y.long(), deepsup=True)
+        loss = out["loss"] if isinstance(out, dict) else out
+        if sc.mode == "bwd":
+            loss.backward()
+        dgamma = sc.fold_step()
+        if sc.mode == "bwd":
+            average_over_ranks(dgamma, self.group)
+            sc.eic_step(dgamma)
+        return loss.detach()
+
+    def close(self):
+        if self.closed:
+            return
+        self.closed = True
+        self.scorer.detach()
+        self.model.train(self._was_training)
+        self.model.zero_grad(set_to_none=True)
+        if self._saved is not None:
+            with torch.no_grad():
+                for m, mean, var, nbt in self._saved:
+                    m.running_mean.copy_(mean)
+                    m.running_var.copy_(var)
+                    m.num_batches_tracked.copy_(nbt)
+
+
+def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, flush_bytes=1 << 30,
+                          return_class_stats=False, seed=0):
+    """Public end-to-end call: HOST images [n,3,H,W] / labels [n,H,W] -> EIC scores on the host.
+
+    Every step copies its micro-batch host->device from pinned memory and reads the step's loss back;
+    with torch.distributed initialised the micro-batches are dealt round-robin (`shard_plan`).  Returns
+    {'eic': {bn_name: FloatTensor[C] (cpu)}, '_stats': {...}} -- `{'eic': ...}` is score.pth's layout."""
     ops.require_gpu()
     device = next(model.parameters()).device
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     world = torch.distributed.get_world_size() if dist_on else 1
     rank = torch.distributed.get_rank() if dist_on else 0
-    scorer = ClassStatsScorer(model, num_classes, mode="bwd", r=r).attach()
-    saved = None
-    if restore_bn_stats:
-        saved = [(m, m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone())
-                 for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.running_mean is not None]
-    was_training = model.training
-    model.train()
-    gamma = torch.cat([m.weight.detach().reshape(-1) for _, m in scorer.layers]).float()
-    n = images.shape[0]
-    n_steps = n // (micro_batch * world)
+    plan = shard_plan(images.shape[0], micro_batch, world, rank)
+    run = CalibrationRun(model, num_classes, r=r, restore_bn_stats=restore_bn_stats, flush_bytes=flush_bytes,
+                         keep_totals=return_class_stats, seed=seed)
     h2d = d2h = 0
+    losses = torch.empty(max(len(plan), 1), dtype=torch.float32).pin_memory()
+    launches0 = ops.launch_count()
     try:
-        for step in range(n_steps):
-            lo = (step * world + rank) * micro_batch
-            xb, yb = images[lo:lo + micro_batch], labels[lo:lo + micro_batch]
-            if pin and not xb.is_pinned():
+        for step, (lo, hi) in enumerate(plan):
+            xb, yb = images[lo:hi], labels[lo:hi]
+            if not xb.is_pinned():
                 xb, yb = xb.pin_memory(), yb.pin_memory()
             x = xb.to(device, non_blocking=True)
             y = yb.to(device, non_blocking=True)
             h2d += xb.numel() * xb.element_size() + yb.numel() * yb.element_size()
-            scorer.zero_stats()
-            scorer.set_labels(y)
-            model.zero_grad(set_to_none=True)
-            loss = model(x, y.long(), deepsup=True)
-            loss = loss["loss"] if isinstance(loss, dict) else loss
-            loss.backward()
-            dgamma = scorer.dgamma()
-            if world > 1:
-                torch.distributed.all_reduce(dgamma)
-                dgamma /= world
-            scorer.eic_step(dgamma, gamma)
+            loss = run.step(x, y, mb_index=lo // micro_batch)
+            losses[step:step + 1].copy_(loss.reshape(1), non_blocking=True)
+            d2h += 4
+        if return_class_stats:
+            run.scorer.all_reduce_totals()
     finally:
-        scorer.detach()
-        model.train(was_training)
-        if saved is not None:
-            with torch.no_grad():
-                for m, mean, var, nbt in saved:
-                    m.running_mean.copy_(mean)
-                    m.running_var.copy_(var)
-                    m.num_batches_tracked.copy_(nbt)
-    out = {"eic": {k: v.cpu() for k, v in scorer.eic_dict()["eic"].items()}}
-    d2h += scorer.eic.numel() * 4
-    out["_stats"] = dict(steps=n_steps, h2d_bytes=h2d, d2h_bytes=d2h, launches=scorer.launches)
+        run.close()
+    sc = run.scorer
+    out = {"eic": {k: v.cpu() for k, v in sc.eic_dict()["eic"].items()}}
+    d2h += sc.eic.numel() * 4
+    if return_class_stats:
+        stats, cnt = sc.class_stats()
+        out["class_stats"] = {k: (a.cpu(), b.cpu()) for k, (a, b) in stats.items()}
+        out["class_counts"] = {k: v.cpu() for k, v in cnt.items()}
+    torch.cuda.synchronize(device)
+    out["_stats"] = dict(steps=len(plan), h2d_bytes=h2d, d2h_bytes=d2h, launches=ops.launch_count() - launches0,
+                         losses=losses[:len(plan)].clone())
     return out

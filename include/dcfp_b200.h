@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DCFP_ABI_VERSION 1
+#define DCFP_ABI_VERSION 2
 
 /* element types of feature maps / weights */
 #define DCFP_F32 0
@@ -38,6 +38,10 @@ extern "C" {
 /* feature-map layouts */
 #define DCFP_NCHW 0
 #define DCFP_NHWC 1 /* torch.channels_last */
+/* meaning of dcfp_layer_desc.scale / .shift */
+#define DCFP_AFFINE_SCALE_SHIFT 0 /* xa = x * scale[c] + shift[c]                                     */
+#define DCFP_AFFINE_INVSTD_MEAN 1 /* xa = (x - shift[c]) * scale[c]: scale = invstd, shift = batch mean,
+                                     i.e. the two vectors autograd's BN node saved -- no host-side prep */
 
 #define DCFP_EINVAL (-1)      /* bad argument (null pointer, non-positive extent, unknown enum) */
 #define DCFP_EUNSUPPORTED (-2) /* valid but not implemented combination */
@@ -59,9 +63,11 @@ int dcfp_label_keys(const void* label, int label_dtype, int N, int H0, int W0, i
  * One scored feature map (one BN layer of one micro-batch).
  *
  * value functor, per element of channel c at pixel p:
- *   forward  (dy == NULL):  v = x * scale[c] + shift[c]            (scale/shift NULL -> 1 / 0)
- *   backward (dy != NULL):  v = dy * (x * scale[c] + shift[c])     with scale = invstd,
- *                           shift = -mean * invstd  => v = dy * xhat, and
+ *   forward  (dy == NULL):  v = xa = x * scale[c] + shift[c]       (scale/shift NULL -> 1 / 0;
+ *                                                                   see affine_mode)
+ *   backward (dy != NULL):  v = dy * xa     with scale = invstd, shift = -mean * invstd (or
+ *                           affine_mode = DCFP_AFFINE_INVSTD_MEAN and shift = mean)
+ *                           => v = dy * xhat, and
  *                           sum_k S1[k][c] == d(loss)/d(gamma_c)   (BN backward, the quantity
  *                           pruners/dcfp_pruner.py:18 reads as m.weight.grad)
  * class key:  keys[n][p] from dcfp_label_keys at this layer's (h, w); key >= K is dropped.
@@ -81,6 +87,8 @@ typedef struct dcfp_layer_desc {
   int32_t dtype;  /* DCFP_F32 | DCFP_BF16 */
   int32_t layout; /* DCFP_NCHW | DCFP_NHWC */
   int32_t ld;     /* row stride of S1/S2 in elements (0 -> C): lets all layers share one [K, sum C] arena */
+  int32_t affine_mode; /* DCFP_AFFINE_SCALE_SHIFT | DCFP_AFFINE_INVSTD_MEAN */
+  int32_t reserved;    /* must be 0 */
 } dcfp_layer_desc;
 
 /* ---- K1: label-keyed segmented reduction over conv/BN feature maps -------------------------
@@ -105,6 +113,10 @@ int dcfp_eic_update_flat(const float* grad, const float* gamma, float* eic, int 
 /* dgamma[c] = sum_k S1[k*C + c]  (fp64 arena -> fp32), the bridge from K1-backward to K2a; C may be
  * the total channel count of a shared [K, sum C] arena (one launch for all layers).             */
 int dcfp_reduce_classes(const double* S1, int K, int C, float* out, void* stream);
+/* End-of-step fold of a per-step arena, ONE launch:  dgamma[c] = sum_k step[0][k][c];
+ * total[m][k][c] += step[m][k][c] for both moments m in {0,1};  step[m][k][c] = 0.
+ * step / total: fp64 [2][K][C] (S1 rows then S2 rows).  total may be NULL (no pass-wide stats). */
+int dcfp_fold_step(double* step, double* total, int K, int C, float* dgamma, void* stream);
 
 /* ---- K2b: global threshold + keep masks -- pruners/dcfp_pruner.py:43-92 ------------------------
  * score: concatenated fp32 scores of the n_layers scored layers; layer l owns

@@ -1,0 +1,167 @@
+"""The calibration scorer on the GPU: K1-bwd summed over classes vs autograd's bn.weight.grad (the quantity
+pruners/dcfp_pruner.py:18 reads), EIC from K2 bit-exact given those gradients, deferred vs immediate launches,
+class statistics vs the oracle on real feature maps, and the public HOST->HOST call.
+
+Tolerance for dgamma: |a - b| <= 2e-4*|b| + 2e-4*mean|b| per layer -- both sides are
+fp32 reductions over up to 2.6e5 terms in different orders (cuDNN's vs K1's fp32-in-CTA / fp64-across-CTA)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import class_stats_ref, eic_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+K, H, W = 19, 128, 256
+
+
+def _setup(arch="deeplabv3", backbone="resnet50", classes=K, seed=0):
+    from dcfp_b200.workloads.segnets import build_segnet
+    return build_segnet(arch, backbone, classes, seed=seed).to(DEV)
+
+
+def _batch(idx, classes=K, h=H, w=W, valid_only=False):
+    from dcfp_b200.workloads.synthetic import synthetic_batch
+    x, y = synthetic_batch(idx, classes, h, w)
+    if valid_only:
+        y = torch.where(y == 255, torch.zeros_like(y), y)
+    return x, y
+
+
+def _close(a, b, rtol=2e-4):
+    scale = np.abs(b).mean()
+    return np.abs(a - b) <= rtol * np.abs(b) + rtol * scale
+
+
+@pytest.mark.parametrize("flush_bytes", [0, 1 << 30, 64 << 20])
+@pytest.mark.parametrize("arch,classes", [("deeplabv3", 19), ("psp", 150), ("deeplabv3p", 171)])
+def test_dgamma_equals_autograd_and_eic_bits(native, arch, classes, flush_bytes):
+    from dcfp_b200.scorer import CalibrationRun
+    model = _setup(arch, "resnet50", classes)
+    x, y = _batch([0, 1], classes, valid_only=True)
+    run = CalibrationRun(model, classes, r=0.999, flush_bytes=flush_bytes, seed=3)
+    run.step(x.to(DEV), y.to(DEV), mb_index=0)
+    sc = run.scorer
+    S1 = sc.totals[0].sum(0).cpu().numpy()
+    assert float(sc.step_arena.abs().sum()) == 0.0  # the fold zeroes the step arena
+    pos = 0
+    for name, m in sc.layers:
+        c = m.weight.numel()
+        g = m.weight.grad.detach().cpu().numpy()
+        ok = _close(S1[pos:pos + c], g)
+        assert ok.all(), "%s: %d / %d channels off, worst %.3g" % (name, (~ok).sum(), c, np.abs(S1[pos:pos + c] - g).max())
+        pos += c
+    exp = eic_ref.eic_step(0, S1.astype(np.float32), sc.gamma().cpu().numpy(), 0.999)
+    assert np.array_equal(sc.eic.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+    # a second step exercises the EMA branch with the previous state
+    prev = sc.eic.cpu().numpy().copy()
+    x2, y2 = _batch([2, 3], classes, valid_only=True)
+    run.step(x2.to(DEV), y2.to(DEV), mb_index=1)
+    S1b = (sc.totals[0].sum(0).cpu().numpy() - S1.astype(np.float64))
+    exp2 = eic_ref.eic_step(prev, S1b.astype(np.float32), sc.gamma().cpu().numpy(), 0.999)
+    got2 = sc.eic.cpu().numpy()
+    # S1b is reconstructed from fp64 totals: the fp32 rounding of dgamma may differ by one ulp -> compare to 1e-6
+    assert np.allclose(got2, exp2, rtol=1e-5, atol=1e-12)
+    run.close()
+    assert all(m.weight.grad is None for _, m in sc.layers)
+
+
+def test_ignored_pixels_are_dropped_and_counts_match(native):
+    """With label 255 present: per-class sums equal the oracle on the same device tensors (captured by hooks),
+    counts equal the oracle's bincount per resolution."""
+    from dcfp_b200.scorer import CalibrationRun
+    model = _setup()
+    x, y = _batch([4, 5])
+    captured = {}
+    target = "backbone.layer2.1.bn2"
+    bn = model.get_submodule(target)
+
+    def fwd_hook(mod, inp, out):
+        captured["x"] = inp[0].detach().clone()
+        out.register_hook(lambda g: captured.__setitem__("dy", g.detach().clone()))
+
+    h = bn.register_forward_hook(fwd_hook)
+    run = CalibrationRun(model, K, seed=1)
+    run.step(x.to(DEV), y.to(DEV), mb_index=0)
+    h.remove()
+    stats, cnt = run.scorer.class_stats()
+    xs, dy = captured["x"].cpu(), captured["dy"].cpu()
+    mean = xs.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(xs.var(dim=(0, 2, 3), unbiased=False) + bn.eps)
+    rc, r1, r2 = class_stats_ref.class_stats_bwd(xs, dy, mean, invstd, y, K)
+    mass = class_stats_ref.abs_mass(class_stats_ref.functor_bwd(xs, dy, invstd, -mean * invstd), y, K)
+    S1, S2 = stats[target]
+    assert ((S1.cpu() - r1).abs() <= 2e-5 * mass + 1e-30).all()
+    assert ((S2.cpu() - r2).abs() <= 2e-5 * r2 + 1e-30).all()
+    hw = tuple(xs.shape[2:])
+    assert torch.equal(cnt[hw].cpu(), rc)
+    for (hh, ww), c in cnt.items():
+        lab = class_stats_ref.nearest_labels(y, hh, ww)
+        assert torch.equal(c.cpu(), torch.bincount(lab[lab < K].reshape(-1), minlength=K).double())
+    run.close()
+
+
+def test_forward_mode_class_statistics(native):
+    """north_star-literal mode: per-class sums / second moments of the BN OUTPUT (pre-ReLU), read once in the hook."""
+    from dcfp_b200.scorer import CalibrationRun
+    model = _setup()
+    x, y = _batch([6, 7])
+    target = "backbone.layer3.2.bn1"
+    bn = model.get_submodule(target)
+    captured = {}
+    h = bn.register_forward_hook(lambda m, i, o: captured.__setitem__("y", o.detach().clone()))
+    run = CalibrationRun(model, K, mode="fwd")
+    with torch.no_grad():
+        run.step(x.to(DEV), y.to(DEV))
+    h.remove()
+    stats, cnt = run.scorer.class_stats()
+    rc, r1, r2 = class_stats_ref.class_stats_fwd(captured["y"].cpu(), y, K)
+    mass = class_stats_ref.abs_mass(captured["y"].cpu(), y, K)
+    S1, S2 = stats[target]
+    assert ((S1.cpu() - r1).abs() <= 1e-5 * mass + 1e-30).all() and ((S2.cpu() - r2).abs() <= 1e-5 * r2 + 1e-30).all()
+    run.close()
+
+
+def test_score_calibration_set_host_api_and_bn_stats_restored(native):
+    from dcfp_b200.scorer import score_calibration_set
+    model = _setup()
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    x, y = _batch(list(range(6)))
+    out = score_calibration_set(model, x, y, K, micro_batch=2, r=0.999, return_class_stats=True, seed=5)
+    st = out["_stats"]
+    assert st["steps"] == 3 and st["h2d_bytes"] == x.numel() * 4 + y.numel() and st["launches"] > 0
+    assert torch.isfinite(st["losses"]).all()
+    assert list(out["eic"].keys()) == [n for n, m in model.named_modules()
+                                       if isinstance(m, torch.nn.BatchNorm2d) and n not in model.ignore_prune_layer]
+    assert all(v.device.type == "cpu" and v.dtype == torch.float32 for v in out["eic"].values())
+    after = model.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before), "scoring must not change weights or BN running stats"
+    # deterministic given the seed (dropout keyed by the global micro-batch index)
+    out2 = score_calibration_set(model, x, y, K, micro_batch=2, r=0.999, seed=5, flush_bytes=0)
+    for k in out["eic"]:
+        assert np.allclose(out["eic"][k].numpy(), out2["eic"][k].numpy(), rtol=1e-3, atol=1e-9), k
+    frac_zero = np.mean(np.concatenate([v.numpy() for v in out["eic"].values()]) == 0)
+    assert 0.02 < frac_zero < 0.5  # ~2^-3 of channels fail the sign gate three times
+
+
+def test_dcfp_pruning_step_api_matches_scorer(native):
+    """The reference-shaped accumulator `pruners.dcfp_pruning` (fed by autograd's weight.grad) and the K1 scorer
+    agree to the dgamma tolerance on the same step."""
+    from dcfp_b200.pruners import dcfp_pruning
+    from dcfp_b200.scorer import CalibrationRun
+    model = _setup()
+    x, y = _batch([8, 9], valid_only=True)
+    tp = dcfp_pruning(model, 0.999)
+    run = CalibrationRun(model, K, r=0.999, seed=9)
+    run.step(x.to(DEV), y.to(DEV), mb_index=0)
+    tp.step(model)  # grads are still attached
+    sc = run.scorer
+    mine = sc.eic_dict()["eic"]
+    theirs = tp.get_eic()["eic"]
+    assert list(mine.keys()) == list(theirs.keys())
+    bad = 0
+    for n in mine:
+        a, b = mine[n].cpu().numpy(), theirs[n].cpu().numpy()
+        bad += int((~_close(a, b, 5e-4)).sum())
+    assert bad <= 5, "%d channels differ (sign-gate flips at |dgamma| ~ 0 are the only legitimate ones)" % bad
+    run.close()

@@ -1,0 +1,137 @@
+"""Checks that need the UNMODIFIED reference tree (build container only; skipped on the GPU box):
+the workload nets equal the reference's, the product's host logic equals a live reference run, and the
+reference's own prune.py runs unmodified against the drop-in `pruners` package."""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from fake_backend import oracle_backend
+from oracle import ref_compat
+
+pytestmark = pytest.mark.ref
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("arch,K", [("deeplabv3", 19), ("psp", 150), ("deeplabv3p", 171)])
+def test_workload_nets_equal_reference(arch, K):
+    """Same module names, bit-identical random-init weights and bit-identical CPU outputs."""
+    from dcfp_b200.workloads import segnets
+    ref = ref_compat.load_reference()
+    torch.manual_seed(0)
+    m_ref = getattr(ref.networks, arch).Seg_Model(backbone="resnet50", backbone_para=dict(segnets.BACKBONE_PARA), model_para={},
+                                                  num_classes=K, align_corner=True, criterion=None, deepsup=True)
+    m = segnets.build_segnet(arch, "resnet50", K, seed=0, with_loss=False)
+    sd_r, sd = m_ref.state_dict(), m.state_dict()
+    assert list(sd_r.keys()) == list(sd.keys())
+    assert all(torch.equal(sd_r[k], sd[k]) for k in sd)
+    assert m.ignore_prune_layer == m_ref.ignore_prune_layer
+    m.eval()
+    m_ref.eval()
+    x = torch.randn(2, 3, 64, 96)
+    with torch.no_grad():
+        a, b = m_ref(x, deepsup=True), m(x, deepsup=True)
+    assert all(torch.equal(i, j) for i, j in zip(a, b))
+
+
+def test_calibration_loss_equals_reference_criterion():
+    import types
+    from dcfp_b200.workloads.segnets import CalibrationLoss
+    ref = ref_compat.load_reference()
+    crit = ref.crit.CriterionDSN(dataset=types.SimpleNamespace(ignore_label=255))
+    preds = [torch.randn(2, 19, 16, 16), torch.randn(2, 19, 16, 16)]
+    y = torch.randint(0, 19, (2, 16, 16))
+    y[0, :3] = 255
+    assert torch.equal(crit(preds, y)["loss"], CalibrationLoss()(preds, y)["loss"])
+
+
+def test_eic_step_live_reference():
+    """dcfp_pruning state layout + oracle eic_ref vs the live reference on a model's real gradient layout."""
+    from oracle import eic_ref
+    ref = ref_compat.load_reference()
+    model = gu.build_model("c1")
+    tp = ref.dp.dcfp_pruning(model, 0.999)
+    from dcfp_b200.pruners import dcfp_pruning
+    mine = dcfp_pruning(model, 0.999)
+    assert list(tp.state_dict["eic"].keys()) == list(mine.state_dict["eic"].keys())
+    assert all(v == 0 and isinstance(v, int) for v in mine.state_dict["eic"].values())
+    rng = np.random.RandomState(0)
+    state = {n: 0 for n in tp.state_dict["eic"]}
+    for step in range(3):
+        for n in state:
+            m = model.get_submodule(n)
+            m.weight.grad = torch.from_numpy((rng.standard_normal(m.weight.numel()) * 1e-4).astype(np.float32))
+        tp.step(model)
+        for n in state:
+            m = model.get_submodule(n)
+            state[n] = eic_ref.eic_step(state[n], m.weight.grad.numpy(), m.weight.detach().numpy(), 0.999)
+            assert np.array_equal(state[n].view(np.uint32), tp.get_eic()["eic"][n].numpy().view(np.uint32))
+
+
+def test_prune_model_live_reference_c1():
+    ref = ref_compat.load_reference()
+    base = gu.build_model("c1", beta_seed=11)
+    eic = gu.make_scores(base, "uniform", 21)
+    path = "/tmp/_live_score.pth"
+    torch.save({"eic": {k: torch.from_numpy(v) for k, v in eic.items()}}, path)
+    gp = 0.5 + 0.02 + 0.02 + 0.02
+    ma, mb = copy.deepcopy(base), copy.deepcopy(base)
+    pr = ref.dp.DCFPPruner(global_percent=gp, layer_keep=0.02, score_file=path)
+    sub_r, cfg_r = pr.prune_model(ma, except_start_keys=["conv_deepsup"])
+    with oracle_backend():
+        from dcfp_b200.pruners.dcfp_pruner import DCFPPruner
+        pm = DCFPPruner(global_percent=gp, layer_keep=0.02, score_file=path)
+        sub_m, cfg_m = pm.prune_model(mb, except_start_keys=["conv_deepsup"])
+        t_m = pm.get_thresh()
+    assert [float(t) for t in pr.get_thresh()] == [float(t) for t in t_m]
+    assert list(pr.norm_conv_links.items()) == list(pm.norm_conv_links.items())
+    assert pr.except_layers == pm.except_layers
+    assert list(cfg_r.keys()) == list(cfg_m.keys())
+    for k in cfg_r:
+        assert list(cfg_r[k].keys()) == list(cfg_m[k].keys()), k
+        for kk, a in cfg_r[k].items():
+            b = cfg_m[k][kk]
+            assert (np.array_equal(a, b) and a.dtype == b.dtype and a.shape == b.shape) if isinstance(a, np.ndarray) else a == b, (k, kk)
+    sr, sm = sub_r.state_dict(), sub_m.state_dict()
+    assert list(sr.keys()) == list(sm.keys())
+    for k in sr:
+        if torch.equal(sr[k], sm[k]):
+            continue
+        assert k.endswith("running_mean") or k in ("last_conv.6.bias", "conv_deepsup.4.bias"), k  # fp32 GEMV of the compensation
+        assert torch.allclose(sr[k], sm[k], rtol=1e-4, atol=1e-5), k
+
+
+def test_reference_prune_py_runs_unmodified_against_dropin(tmp_path):
+    """`prune.py` of the reference, byte-for-byte, once with its own `pruners` and once with the drop-in:
+    same global_percent trajectory, bit-identical pruned.pth and channel_cfg.pth."""
+    model = gu.build_model("c1")
+    sd = {k: v for k, v in model.state_dict().items()}
+    ckpt, score = str(tmp_path / "model.pth"), str(tmp_path / "score.pth")
+    torch.save(sd, ckpt)
+    eic = gu.make_scores(model, "uniform", 31)
+    torch.save({"eic": {k: torch.from_numpy(v) for k, v in eic.items()}}, score)
+    outs = {}
+    for which in ("reference", "dropin"):
+        save = str(tmp_path / which)
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "run_reference_cli.py"), which, "--oracle-backend",
+               os.path.join(ref_compat.REF_ROOT, "prune.py"), "--model", "deeplabv3", "--backbone", "resnet50",
+               "--backbone-para", '{"os": 8, "mg_unit": [1,2,4], "inplanes": 128, "pretrained": false}',
+               "--dataset", "CS", "--prune-ratio", "0.45", "--model-path", ckpt, "--score-path", score, "--save-path", save]
+        p = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=900)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        lines = [l for l in p.stdout.splitlines() if l.startswith(("global_percent", "flops", "Finish"))]
+        outs[which] = (lines, torch.load(os.path.join(save, "pruned.pth"), weights_only=False),
+                       torch.load(os.path.join(save, "channel_cfg.pth"), weights_only=False))
+    assert outs["reference"][0] == outs["dropin"][0] and any(l.startswith("Finish") for l in outs["dropin"][0])
+    a, b = outs["reference"][1], outs["dropin"][1]
+    assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+    ca, cb = outs["reference"][2], outs["dropin"][2]
+    assert list(ca.keys()) == list(cb.keys())
+    for k in ca:
+        for kk, v in ca[k].items():
+            assert np.array_equal(v, cb[k][kk]) if isinstance(v, np.ndarray) else v == cb[k][kk]
