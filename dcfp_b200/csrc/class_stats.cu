@@ -190,7 +190,10 @@ struct BoxCursor {
   }
 };
 
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS>
+// RUNLEN: keep the current class run (key, sum, sum of squares) in registers and touch the shared table only
+// when the class changes -- the table of the large-K variant is updated with shared atomics (2 x ~64 cycles
+// per warp-wide update), so the number of updates, not of pixels, is what it can afford.
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, bool RUNLEN>
 __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMap* maps, const int K, const int stages,
                                              const int tile, unsigned char* smem) {
   constexpr int kBoxPx = kBoxRowBytes / static_cast<int>(sizeof(T));  // 32 (fp32) / 64 (bf16)
@@ -275,6 +278,21 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   const uint32_t row_off = static_cast<uint32_t>(lane * kBoxRowBytes);
   const uint32_t l7 = static_cast<uint32_t>(lane & 7);
 
+  // run state (RUNLEN only): class of the open run (K = none / dropped) and its partial sums
+  unsigned run_key = static_cast<unsigned>(K);
+  float run1 = 0.f, run2 = 0.f;
+  auto run_add = [&](unsigned key, float a1, float a2) {  // key is warp-uniform: no divergence
+    if (key != run_key) {
+      if (run_key < static_cast<unsigned>(K)) acc_add<SHARED_ACC>(acc_lane, run_key, run1, run2);
+      run_key = key;
+      run1 = a1;
+      run2 = a2;
+    } else {
+      run1 += a1;
+      run2 += a2;
+    }
+  };
+
   int stage = 0;
   uint32_t parity = 0;
   for (int it = 0; it < n_my; ++it) {
@@ -302,7 +320,10 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
         }
         s1a = add2(s1a, s1b);
         s2a = add2(s2a, s2b);
-        acc_add<SHARED_ACC>(acc_lane, key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
+        if (RUNLEN) run_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
+        else acc_add<SHARED_ACC>(acc_lane, key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
+      } else if (RUNLEN) {
+        run_add(static_cast<unsigned>(K), 0.f, 0.f);  // dropped pixels close the open run
       }
     } else {
       // a class boundary crosses the box: per quad (4 px, one packed key word) -- a quad with one
@@ -320,7 +341,10 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
             if (key < static_cast<unsigned>(K)) {
               const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
               const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
-              acc_add<SHARED_ACC>(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+              if (RUNLEN) run_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+              else acc_add<SHARED_ACC>(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+            } else if (RUNLEN) {
+              run_add(static_cast<unsigned>(K), 0.f, 0.f);
             }
           } else {
 #pragma unroll 1
@@ -328,7 +352,10 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
               const unsigned ke = (wv >> (8 * e)) & 0xffu;
               if (ke < static_cast<unsigned>(K)) {
                 const float x = load_px<T, BWD, AFFINE>(gaddr + (h * 4 + e) * static_cast<int>(sizeof(T)), sc, sf);
-                acc_add<SHARED_ACC>(acc_lane, ke, x, x * x);
+                if (RUNLEN) run_add(ke, x, x * x);
+                else acc_add<SHARED_ACC>(acc_lane, ke, x, x * x);
+              } else if (RUNLEN) {
+                run_add(static_cast<unsigned>(K), 0.f, 0.f);
               }
             }
           }
@@ -343,6 +370,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
       parity ^= 1u;
     }
   }
+  if (RUNLEN) run_add(static_cast<unsigned>(K), 0.f, 0.f);  // close the last run
   __syncthreads();
 
   // ---- CTA partials -> fp64 arena (coalesced RED.F64; zero partials are skipped) ----------------
@@ -363,7 +391,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   }
 }
 
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL>
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL, bool RUNLEN>
 __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
     class_stats_kernel(const __grid_constant__ GroupParams<MAXL, BWD ? 2 : 1> P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -376,7 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
     if (P.tile_prefix[mid] <= tile) lo = mid;
     else hi = mid;
   }
-  process_tile<T, BWD, AFFINE, SHARED_ACC, WARPS>(P.L[lo], &P.maps[lo * (BWD ? 2 : 1)], P.K, P.stages, tile - P.tile_prefix[lo],
+  process_tile<T, BWD, AFFINE, SHARED_ACC, WARPS, RUNLEN>(P.L[lo], &P.maps[lo * (BWD ? 2 : 1)], P.K, P.stages, tile - P.tile_prefix[lo],
                                                   smem);
 }
 
@@ -557,7 +585,7 @@ int launch_tiled(GroupParams<MAXL, BWD ? 2 : 1>& P, int n_tiles, cudaStream_t st
   constexpr int kWarpsT = SHARED_ACC ? kWarpsShared : kWarpsPrivate;
   P.stages = pick_stages();
   const size_t smem = tile_smem_bytes(P.K, BWD, SHARED_ACC, P.stages);
-  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL>;
+  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL, SHARED_ACC>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
   kern<<<n_tiles, kWarpsT * 32, smem, stream>>>(P);
