@@ -10,7 +10,8 @@ dev = torch.device("cuda")
 K = int(os.environ.get("K", 19))
 bwd = os.environ.get("BWD", "0") == "1"
 dtype = torch.bfloat16 if os.environ.get("DT", "f32") == "bf16" else torch.float32
-_, lab = synthetic_batch([0, 1], K, 512, 1024)
+S = 1 if K == 19 else 2  # 512x1024 (Cityscapes) vs 512x512 (ADE / COCO-Stuff) label maps
+_, lab = synthetic_batch([0, 1], K, 512, 1024 // S)
 lab = lab.to(dev)
 KEYS = {}
 def keys_for(shapes):
@@ -20,7 +21,8 @@ def keys_for(shapes):
             KEYS[(h, w)] = ops.label_keys(lab, h, w, K)
         out.append(KEYS[(h, w)])
     return out
-shapes = [(1024, 64, 128)] * 5 + [(256, 64, 128)] * 12 + [(512, 64, 128)] * 3 + [(2048, 64, 128)] + [(256, 128, 256)] + [(64, 256, 512)]
+shapes = [(1024, 64, 128 // S)] * 5 + [(256, 64, 128 // S)] * 12 + [(512, 64, 128 // S)] * 3 + [(2048, 64, 128 // S)] + \
+    [(256, 128, 256 // S)] + [(64, 256, 512 // S)]
 xs = [torch.randn(2, c, h, w, device=dev).to(dtype) for c, h, w in shapes]
 dys = [torch.randn_like(x) for x in xs] if bwd else None
 sc = [torch.ones(c, device=dev) for c, _, _ in shapes] if bwd else None
