@@ -408,6 +408,250 @@ __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
                                                   smem);
 }
 
+// ---- channels_last (NHWC) path ---------------------------------------------------------------------
+// x[n][p][c] with C contiguous: every pixel has ONE class for all its channels, so with lane = 4 consecutive
+// channels the class key is warp-uniform by construction and the loads are coalesced as they are -- no
+// shared-memory transposition, no TMA staging.  A warp streams the pixels of its [128-channel slab] with
+// 128-bit (fp32) / 64-bit (bf16) loads, software-pipelined one pixel group ahead, and keeps the OPEN CLASS RUN
+// (sum, sum of squares of its 4 channels) in registers; its private [K][2][128] fp32 table in shared memory is
+// touched only when the class changes.  A CTA's 8 warps cover `spc` adjacent slabs x 8/spc pixel phases, so a
+// CTA reads one fully contiguous range of memory.  cuDNN's tensor-core convolutions are NHWC-native: running
+// the feature-map producer in channels_last removes its layout transposes (measured 52 -> 35 ms per c2 step),
+// which is why this is the layout bench.py scores.
+constexpr int kNhwcWarps = 8;
+constexpr int kNhwcSlab = 128;      // channels per warp row: 32 lanes x 4
+constexpr int kNhwcMaxK = 27;       // 8 warps x K x 1 KB of tables must fit in 227 KB
+
+struct NhwcLayer {
+  const void* x;
+  const void* dy;
+  const uint8_t* keys;  // [N*HW]
+  const float* scale;
+  const float* shift;
+  double* S1;
+  double* S2;
+  int32_t C, ld, centered;
+  int32_t n_px;           // N * HW
+  int32_t spc;            // slabs per CTA: 1, 2, 4 or 8
+  int32_t n_slab_groups;  // ceil(ceil(C / 128) / spc)
+  int32_t px_per_chunk;   // multiple of 16 * (8 / spc)
+  int32_t n_chunks;
+};
+template <int MAXL>
+struct NhwcParams {
+  NhwcLayer L[MAXL];
+  int32_t tile_prefix[MAXL + 1];
+  int32_t n_layers;
+  int32_t K;
+};
+constexpr int kNhwcBigGroup = 160;
+
+// 4 channels of one pixel as two packed fp32 pairs
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw load(const void* base, size_t elem) {
+    return ldg_stream128(static_cast<const float*>(base) + elem);
+  }
+  __device__ static __forceinline__ void unpack(const Raw& r, f2& a, f2& b) {
+    a = static_cast<f2>(r.x) | (static_cast<f2>(r.y) << 32);
+    b = static_cast<f2>(r.z) | (static_cast<f2>(r.w) << 32);
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  using Raw = uint2;
+  __device__ static __forceinline__ Raw load(const void* base, size_t elem) {
+    Raw v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(v.x), "=r"(v.y)
+                 : "l"(static_cast<const __nv_bfloat16*>(base) + elem));
+    return v;
+  }
+  __device__ static __forceinline__ void unpack(const Raw& r, f2& a, f2& b) {
+    a = Elem<__nv_bfloat16>::widen(r.x);
+    b = Elem<__nv_bfloat16>::widen(r.y);
+  }
+};
+
+template <typename T, bool BWD, int MAXL>
+__global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL> P) {
+  constexpr int G = BWD ? 8 : 16;  // pixels per group (one packed key vector), all loads of a group in flight
+  using V = Vec4<T>;
+  using Raw = typename V::Raw;
+  extern __shared__ __align__(16) float tables[];  // [warp][K][2][128]
+
+  const int tile = blockIdx.x;
+  int lo = 0, hi = P.n_layers;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (P.tile_prefix[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  const NhwcLayer& L = P.L[lo];
+  const int K = P.K;
+  const int t = tile - P.tile_prefix[lo];
+  const int chunk = t / L.n_slab_groups, sg = t - chunk * L.n_slab_groups;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int spc = L.spc, phases = kNhwcWarps / spc;
+  const int slab_local = warp % spc, phase = warp / spc;
+  const int c0 = (sg * spc + slab_local) * kNhwcSlab + lane * 4;
+  const bool lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside
+
+  float* mine = tables + static_cast<size_t>(warp) * K * 256;
+  for (int i = lane; i < K * 64; i += 32) reinterpret_cast<float4*>(mine)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+
+  f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
+  if (lane_on && (BWD || L.scale || L.shift)) {
+    float sc[4], sf[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = L.scale ? L.scale[c0 + j] : 1.f;
+      sf[j] = L.shift ? L.shift[c0 + j] : 0.f;
+      if (L.centered) sf[j] = -sf[j] * sc[j];
+    }
+    sc01 = pack2(sc[0], sc[1]);
+    sc23 = pack2(sc[2], sc[3]);
+    sf01 = pack2(sf[0], sf[1]);
+    sf23 = pack2(sf[2], sf[3]);
+  }
+  const bool affine = BWD || L.scale || L.shift;
+
+  const int p_begin = chunk * L.px_per_chunk;
+  const int p_end = min(p_begin + L.px_per_chunk, L.n_px);
+  const int n_groups = (p_end - p_begin + G - 1) / G;
+  const size_t C = static_cast<size_t>(L.C);
+
+  // open run: class (K = none) and the partial sums of this lane's 4 channels
+  unsigned run_key = static_cast<unsigned>(K);
+  f2 r1a = 0, r1b = 0, r2a = 0, r2b = 0;
+  auto flush = [&]() {
+    if (run_key < static_cast<unsigned>(K)) {
+      float4* row = reinterpret_cast<float4*>(mine + run_key * 256) + lane;
+      float4 a = row[0], b = row[32];
+      a.x += lo2(r1a); a.y += hi2(r1a); a.z += lo2(r1b); a.w += hi2(r1b);
+      b.x += lo2(r2a); b.y += hi2(r2a); b.z += lo2(r2b); b.w += hi2(r2b);
+      row[0] = a;
+      row[32] = b;
+    }
+    r1a = r1b = r2a = r2b = 0;
+  };
+  auto add_px = [&](const Raw& xr, const Raw& dr) {
+    f2 a, b;
+    V::unpack(xr, a, b);
+    if (BWD) {
+      f2 da, db;
+      V::unpack(dr, da, db);
+      a = mul2(da, fma2(a, sc01, sf01));
+      b = mul2(db, fma2(b, sc23, sf23));
+    } else if (affine) {
+      a = fma2(a, sc01, sf01);
+      b = fma2(b, sc23, sf23);
+    }
+    r1a = add2(r1a, a);
+    r1b = add2(r1b, b);
+    r2a = fma2(a, a, r2a);
+    r2b = fma2(b, b, r2b);
+  };
+
+  struct Group {  // one pixel group in registers: every index below is a compile-time constant after unrolling
+    Raw x[G];
+    Raw d[BWD ? G : 1];
+    unsigned long long k[G / 8];  // packed keys; K = dropped
+  };
+  const unsigned long long dropped = static_cast<unsigned long long>(K) * 0x0101010101010101ull;
+  auto load_group = [&](int g, Group& B) {
+    const int p = p_begin + g * G;
+    if (p + G <= p_end) {
+#pragma unroll
+      for (int q = 0; q < G / 8; ++q)
+        B.k[q] = L.keys ? __ldg(reinterpret_cast<const unsigned long long*>(L.keys + p) + q) : 0ull;
+      if (lane_on) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          B.x[i] = V::load(L.x, (p + i) * C + c0);
+          if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
+        }
+      }
+    } else {  // ragged tail of the chunk: pixel by pixel, missing pixels are "dropped"
+#pragma unroll
+      for (int q = 0; q < G / 8; ++q) B.k[q] = dropped;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        if (p + i < p_end) {
+          const unsigned long long k = L.keys ? L.keys[p + i] : 0;
+          const int sh = 8 * (i & 7);
+          B.k[i >> 3] = (B.k[i >> 3] & ~(0xffull << sh)) | (k << sh);
+          if (lane_on) {
+            B.x[i] = V::load(L.x, (p + i) * C + c0);
+            if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
+          }
+        }
+      }
+    }
+  };
+  auto consume = [&](const Group& B) {
+    const unsigned k0 = static_cast<unsigned>(B.k[0] & 0xffull);
+    bool uniform = true;
+#pragma unroll
+    for (int q = 0; q < G / 8; ++q) uniform = uniform && B.k[q] == k0 * 0x0101010101010101ull;
+    if (uniform) {  // the whole group continues (or opens) one run: branch-free accumulate
+      if (k0 != run_key) {
+        flush();
+        run_key = k0;
+      }
+      if (k0 < static_cast<unsigned>(K) && lane_on) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) add_px(B.x[i], B.d[BWD ? i : 0]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const unsigned k = static_cast<unsigned>(B.k[i >> 3] >> (8 * (i & 7))) & 0xffu;
+        if (k != run_key) {
+          flush();
+          run_key = k;
+        }
+        if (k < static_cast<unsigned>(K) && lane_on) add_px(B.x[i], B.d[BWD ? i : 0]);
+      }
+    }
+  };
+
+  // groups of this warp: phase, phase + phases, ...; the next group's loads are in flight while one is consumed
+  Group A, B;
+  int g = phase;
+  if (g < n_groups) load_group(g, A);
+  while (g < n_groups) {
+    if (g + phases < n_groups) load_group(g + phases, B);
+    consume(A);
+    g += phases;
+    if (g >= n_groups) break;
+    if (g + phases < n_groups) load_group(g + phases, A);
+    consume(B);
+    g += phases;
+  }
+  flush();
+  __syncthreads();
+
+  // ---- per-warp tables -> fp64 arena (sum over the pixel phases of each slab; zero partials skipped) ----------
+  const int width = spc * kNhwcSlab;
+  for (int idx = tid; idx < K * 2 * width; idx += kNhwcWarps * 32) {
+    const int cl = idx % width;
+    const int km = idx / width;  // k * 2 + moment
+    const int sl = cl / kNhwcSlab, within = cl - sl * kNhwcSlab;
+    const int c = (sg * spc + sl) * kNhwcSlab + within;
+    if (c >= L.C) continue;
+    float s = 0.f;
+    for (int ph = 0; ph < phases; ++ph) s += tables[static_cast<size_t>(ph * spc + sl) * K * 256 + km * 128 + within];
+    if (s == 0.f) continue;
+    double* dst = (km & 1) ? L.S2 : L.S1;
+    atomicAdd(&dst[static_cast<size_t>(km >> 1) * L.ld + c], static_cast<double>(s));
+  }
+}
+
 // Generic path: any extent / alignment / layout (tiny 1x1..6x6 maps, odd crops, NHWC).  One
 // thread per channel walks the pixels of one plane chunk; runs are flushed straight to the arena.
 struct GenericLayer {
@@ -560,6 +804,65 @@ bool tiled_ok(const dcfp_layer_desc& d) {
   return true;
 }
 
+// the NHWC fast path: whole 4-channel vectors, 16-B aligned rows, per-warp tables that fit in shared memory
+bool nhwc_ok(const dcfp_layer_desc& d) {
+  if (d.layout != DCFP_NHWC || d.K > kNhwcMaxK) return false;
+  const size_t es = d.dtype == DCFP_F32 ? 4 : 2;
+  if (d.C % 4 != 0 || (static_cast<size_t>(d.C) * es) % (4 * es) != 0) return false;
+  const uintptr_t al = 4 * es;  // one lane's vector
+  if (reinterpret_cast<uintptr_t>(d.x) % al != 0) return false;
+  if (d.dy && reinterpret_cast<uintptr_t>(d.dy) % al != 0) return false;
+  if (d.keys && reinterpret_cast<uintptr_t>(d.keys) % 16 != 0) return false;
+  if (static_cast<long long>(d.N) * d.h * d.w < 64) return false;  // tiny pooled maps: generic
+  return true;
+}
+
+template <typename T, bool BWD, int MAXL>
+int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long target_bytes, cudaStream_t stream) {
+  const int K = descs[which[0]].K;
+  NhwcParams<MAXL> P;
+  P.n_layers = n;
+  P.K = K;
+  P.tile_prefix[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const dcfp_layer_desc& d = descs[which[i]];
+    NhwcLayer& L = P.L[i];
+    L.x = d.x;
+    L.dy = d.dy;
+    L.keys = d.keys;
+    L.scale = d.scale;
+    L.shift = d.shift;
+    L.S1 = d.S1;
+    L.S2 = d.S2;
+    L.C = d.C;
+    L.ld = d.ld > 0 ? d.ld : d.C;
+    L.centered = d.affine_mode == DCFP_AFFINE_INVSTD_MEAN;
+    L.n_px = d.N * d.h * d.w;
+    const int n_slabs = (d.C + kNhwcSlab - 1) / kNhwcSlab;
+    int spc = 1;
+    while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
+    L.spc = spc;
+    L.n_slab_groups = (n_slabs + spc - 1) / spc;
+    const int gran = (BWD ? 8 : 16) * (kNhwcWarps / spc);  // every phase gets whole pixel groups
+    const long long row_bytes = static_cast<long long>(std::min(d.C, spc * kNhwcSlab)) * sizeof(T);
+    long long px = std::max<long long>(target_bytes / row_bytes, gran);
+    px = (px + gran - 1) / gran * gran;
+    L.px_per_chunk = static_cast<int>(std::min<long long>(px, (static_cast<long long>(L.n_px) + gran - 1) / gran * gran));
+    L.n_chunks = (L.n_px + L.px_per_chunk - 1) / L.px_per_chunk;
+    const long long tiles = static_cast<long long>(L.n_chunks) * L.n_slab_groups;
+    DCFP_REQUIRE(P.tile_prefix[i] + tiles < (1LL << 31), DCFP_ETOOBIG, "class_stats: too many tiles");
+    P.tile_prefix[i + 1] = P.tile_prefix[i] + static_cast<int>(tiles);
+  }
+  const int n_tiles = P.tile_prefix[n];
+  if (n_tiles == 0) return 0;
+  const size_t smem = static_cast<size_t>(kNhwcWarps) * K * 256 * sizeof(float);
+  auto kern = class_stats_nhwc_kernel<T, BWD, MAXL>;
+  int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
+  if (rc) return rc;
+  kern<<<n_tiles, kNhwcWarps * 32, smem, stream>>>(P);
+  return finish_launch("class_stats_nhwc");
+}
+
 template <typename T, bool BWD>
 int launch_generic(const dcfp_layer_desc& d, cudaStream_t stream) {
   GenericLayer L{d.x, d.dy, d.keys, d.scale, d.shift, d.S1, d.S2, d.C, d.h * d.w, d.ld > 0 ? d.ld : d.C,
@@ -642,8 +945,9 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
                DCFP_MAX_GROUP_LAYERS);
   const int K = descs[0].K, dtype = descs[0].dtype;
   const bool bwd = descs[0].dy != nullptr;
-  int tiled[DCFP_MAX_GROUP_LAYERS];
-  int n_tiled = 0;
+  int tiled[DCFP_MAX_GROUP_LAYERS], nhwc[DCFP_MAX_GROUP_LAYERS];
+  int n_tiled = 0, n_nhwc = 0;
+  long long nhwc_bytes = 0;
   long long total_boxes = 0;  // boxes x channel groups over the whole call
   const int box_px = kBoxRowBytes / (dtype == DCFP_F32 ? 4 : 2);
   for (int i = 0; i < n_layers; ++i) {
@@ -652,13 +956,41 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
     if (rc) return rc;
     DCFP_REQUIRE(d.K == K && d.dtype == dtype && (d.dy != nullptr) == bwd, DCFP_EINVAL,
                  "class_stats[%d]: K / dtype / functor differ inside one group", i);
-    if (tiled_ok(d)) {
+    if (nhwc_ok(d)) {
+      nhwc[n_nhwc++] = i;
+      nhwc_bytes += static_cast<long long>(d.N) * d.C * d.h * d.w * (dtype == DCFP_F32 ? 4 : 2);
+    } else if (tiled_ok(d)) {
       tiled[n_tiled++] = i;
       total_boxes += ((static_cast<long long>(d.h) * d.w + box_px - 1) / box_px) * d.N * ((d.C + 31) / 32);
     } else {
       if (dtype == DCFP_F32) rc = bwd ? launch_generic<float, true>(d, stream) : launch_generic<float, false>(d, stream);
       else rc = bwd ? launch_generic<__nv_bfloat16, true>(d, stream) : launch_generic<__nv_bfloat16, false>(d, stream);
       if (rc) return rc;
+    }
+  }
+  if (n_nhwc > 0) {
+    // ~1 MB of x per CTA (one CTA per SM), halved while the call cannot fill ~6 waves
+    long long target = 1 << 20;
+    while (target > (64 << 10) && nhwc_bytes / target < 6LL * kNumSMs) target >>= 1;
+    for (int first = 0; first < n_nhwc;) {
+      const int m = std::min(n_nhwc - first, kNhwcBigGroup);
+      int rc;
+      if (m <= kSmallGroup) {
+        if (dtype == DCFP_F32)
+          rc = bwd ? run_nhwc<float, true, kSmallGroup>(descs, nhwc + first, m, target, stream)
+                   : run_nhwc<float, false, kSmallGroup>(descs, nhwc + first, m, target, stream);
+        else
+          rc = bwd ? run_nhwc<__nv_bfloat16, true, kSmallGroup>(descs, nhwc + first, m, target, stream)
+                   : run_nhwc<__nv_bfloat16, false, kSmallGroup>(descs, nhwc + first, m, target, stream);
+      } else if (dtype == DCFP_F32) {
+        rc = bwd ? run_nhwc<float, true, kNhwcBigGroup>(descs, nhwc + first, m, target, stream)
+                 : run_nhwc<float, false, kNhwcBigGroup>(descs, nhwc + first, m, target, stream);
+      } else {
+        rc = bwd ? run_nhwc<__nv_bfloat16, true, kNhwcBigGroup>(descs, nhwc + first, m, target, stream)
+                 : run_nhwc<__nv_bfloat16, false, kNhwcBigGroup>(descs, nhwc + first, m, target, stream);
+      }
+      if (rc) return rc;
+      first += m;
     }
   }
   if (n_tiled == 0) return 0;

@@ -190,9 +190,13 @@ class ClassStatsScorer:
                     else:
                         mean = module.running_mean.float()
                         invstd = torch.rsqrt(module.running_var.float() + module.eps)
-                    g = self._dense(dy)
-                    if xd.stride() != g.stride():
-                        xd, g = xd.contiguous(), g.contiguous()
+                    # K1 wants x and dy in ONE layout: follow x (the tensor autograd saved, never copied)
+                    if xd.is_contiguous():
+                        g = dy.contiguous()
+                    elif xd.is_contiguous(memory_format=torch.channels_last):
+                        g = dy.contiguous(memory_format=torch.channels_last)
+                    else:
+                        xd, g = xd.contiguous(), dy.contiguous()
                     item = (xd, g, invstd.contiguous(), mean.contiguous(), self._keys_for(xd.shape[2], xd.shape[3]), S1, S2)
                     if self.flush_bytes <= 0:
                         self._launch([item])
@@ -315,6 +319,9 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     {'eic': {bn_name: FloatTensor[C] (cpu)}, '_stats': {...}} -- `{'eic': ...}` is score.pth's layout."""
     ops.require_gpu()
     device = next(model.parameters()).device
+    # feed the model in its own memory format (channels_last models: NHWC feature maps, K1's NHWC path)
+    nhwc = any(p.dim() == 4 and p.shape[1] > 1 and p.shape[2] * p.shape[3] > 1 and not p.is_contiguous()
+               and p.is_contiguous(memory_format=torch.channels_last) for p in model.parameters())
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     world = torch.distributed.get_world_size() if dist_on else 1
     rank = torch.distributed.get_rank() if dist_on else 0
@@ -330,6 +337,8 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
             if not xb.is_pinned():
                 xb, yb = xb.pin_memory(), yb.pin_memory()
             x = xb.to(device, non_blocking=True)
+            if nhwc:
+                x = x.contiguous(memory_format=torch.channels_last)
             y = yb.to(device, non_blocking=True)
             h2d += xb.numel() * xb.element_size() + yb.numel() * yb.element_size()
             loss = run.step(x, y, mb_index=lo // micro_batch)

@@ -26,8 +26,12 @@ shapes = [(1024, 64, 128 // s)] * 24 + [(256, 64, 128 // s)] * 52 + [(512, 64, 1
     [(128, 64, 128 // s)] * 7 + [(128, 128, 256 // s)] + [(256, 1, 1)]
 
 
+NHWC = os.environ.get("LAYOUT", "nchw") == "nhwc"
+fmt = torch.channels_last if NHWC else torch.contiguous_format
+
+
 def run(dtype, bwd, iters=5):
-    xs = [torch.randn(mb, c, h, w, device=dev).to(dtype) for c, h, w in shapes]
+    xs = [torch.randn(mb, c, h, w, device=dev).to(dtype).contiguous(memory_format=fmt) for c, h, w in shapes]
     dys = [torch.randn_like(x) for x in xs] if bwd else None
     sc = [torch.ones(c, device=dev) for c, _, _ in shapes] if bwd else None
     sf = [torch.zeros(c, device=dev) for c, _, _ in shapes] if bwd else None
@@ -45,7 +49,7 @@ def run(dtype, bwd, iters=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    print("K=%d %s %s grouped: %.3f ms  %.1f GB/s (%.1f%% of 6551)  %.0f img/s" %
+    print(("nhwc " if NHWC else "nchw ") + "K=%d %s %s grouped: %.3f ms  %.1f GB/s (%.1f%% of 6551)  %.0f img/s" %
           (K, str(dtype).split(".")[-1], "bwd" if bwd else "fwd", ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 65.514, mb / ms * 1e3), flush=True)
     # per-layer launches, the dominant shape
     x = xs[30]

@@ -208,3 +208,65 @@ def test_validation_errors(native):
         ops.class_stats(x, torch.zeros(1, 8, 8, dtype=torch.uint8, device=dev), 19, S[:19], S[:19].clone())
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.class_stats(x.cpu(), None, 1, S[:1], S[:1].clone())
+
+
+NHWC_SHAPES = [
+    # N, C, h, w, H0, W0, K -- channels_last feature maps (the layout bench.py scores: cuDNN's NHWC-native convolutions)
+    (2, 256, 64, 128, 512, 1024, 19),   # 2 slabs x 4 pixel phases
+    (2, 64, 128, 256, 512, 1024, 19),   # one slab, half of the lanes idle
+    (2, 48, 32, 64, 256, 512, 19),      # partial slab
+    (2, 1024, 32, 64, 256, 512, 19),    # 8 slabs, one phase
+    (1, 2048, 16, 32, 128, 256, 19),    # two slab groups
+    (2, 384, 24, 40, 192, 320, 7),      # 3 slabs -> spc 4, one slab of the group is empty
+    (3, 128, 31, 37, 250, 300, 19),     # ragged: n_px not a multiple of the group / chunk
+    (2, 100, 20, 20, 160, 160, 19),     # C % 4 == 0 but not a multiple of the slab
+    (2, 66, 20, 20, 160, 160, 19),      # C % 4 != 0 -> generic path
+    (2, 128, 32, 32, 256, 256, 150),    # K too large for the per-warp tables -> generic path
+    (2, 512, 2, 2, 512, 512, 19),       # tiny pooled map -> generic path
+]
+
+
+@pytest.mark.parametrize("shape", NHWC_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bwd", [False, True])
+def test_channels_last_fast_path(native, shape, dtype, bwd):
+    from dcfp_b200 import ops
+    N, C, h, w, H0, W0, K = shape
+    g = torch.Generator().manual_seed((hash(shape) + bwd) % 2**31)
+    x = (torch.randn(N, C, h, w, generator=g) * 1.5 + 0.3).to(dtype).contiguous(memory_format=torch.channels_last)
+    label = _labels(N, H0, W0, K, torch.uint8, seed=17 + C)
+    if bwd:
+        dy = (torch.randn(N, C, h, w, generator=g) * 1e-3).to(dtype).contiguous(memory_format=torch.channels_last)
+        mean = x.float().mean((0, 2, 3))
+        invstd = 1.0 / torch.sqrt(x.float().var((0, 2, 3), unbiased=False) + 1e-5)
+        _check(ops, x, label, K, dy=dy, scale=invstd, shift=-mean * invstd)
+    else:
+        _check(ops, x, label, K)
+
+
+def test_channels_last_invstd_mean_mode_and_no_keys(native):
+    """affine_mode = INVSTD_MEAN (what the scorer passes: autograd's saved mean / invstd) and keys == None (K == 1)."""
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    N, C, h, w, K = 2, 256, 32, 64, 19
+    g = torch.Generator().manual_seed(41)
+    for layout in (torch.contiguous_format, torch.channels_last):
+        x = (torch.randn(N, C, h, w, generator=g) * 2 + 1).contiguous(memory_format=layout)
+        dy = (torch.randn(N, C, h, w, generator=g) * 1e-3).contiguous(memory_format=layout)
+        mean = x.mean((0, 2, 3))
+        invstd = 1.0 / torch.sqrt(x.var((0, 2, 3), unbiased=False) + 1e-5)
+        label = _labels(N, 256, 512, K, torch.uint8, seed=5)
+        keys = ops.label_keys(label.to(dev), h, w, K)
+        S1 = torch.zeros(K, C, dtype=torch.float64, device=dev)
+        S2 = torch.zeros_like(S1)
+        ops.class_stats(x.to(dev), keys, K, S1, S2, dy=dy.to(dev), scale=invstd.to(dev), shift=mean.to(dev),
+                        affine_mode=ops.AFFINE_INVSTD_MEAN)
+        rc, r1, r2 = ref.class_stats_bwd(x, dy, mean, invstd, label, K)
+        mass = ref.abs_mass(ref.functor_bwd(x, dy, invstd, -mean * invstd), label, K)
+        assert ((S1.cpu() - r1).abs() <= 2 * RTOL * mass + 1e-30).all()
+        assert ((S2.cpu() - r2).abs() <= 2 * RTOL * r2 + 1e-30).all()
+        T1 = torch.zeros(1, C, dtype=torch.float64, device=dev)
+        T2 = torch.zeros_like(T1)
+        ops.class_stats(x.to(dev), None, 1, T1, T2)
+        assert ((T1[0].cpu() - x.double().sum((0, 2, 3))).abs() <= RTOL * x.double().abs().sum((0, 2, 3))).all()
+        assert ((T2[0].cpu() - (x.double() ** 2).sum((0, 2, 3))).abs() <= RTOL * (x.double() ** 2).sum((0, 2, 3))).all()
