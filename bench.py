@@ -264,6 +264,10 @@ def run_b200_arm(args, c):
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     for s in range(args.prime):  # set-up: cuDNN benchmark autotuning + allocator growth, not part of W
         run.step(*resident[s % len(resident)], mb_index=s * world + rank)
+    # cuDNN's autotuning trials leave >100 GB of workspace blocks cached; with a few GB of deferred gradients on top the
+    # caching allocator would garbage-collect inside timed steps.  Release them once; steady state needs ~20 GB.
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     # the EIC state must not see the priming steps: restart the accumulator
     sc.steps = 0
     sc.eic.zero_()

@@ -483,51 +483,33 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
   using Raw = typename V::Raw;
   extern __shared__ __align__(16) float tables[];  // [warp][K][2][128]
 
-  const int tile = blockIdx.x;
-  int lo = 0, hi = P.n_layers;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (P.tile_prefix[mid] <= tile) lo = mid;
-    else hi = mid;
-  }
-  const NhwcLayer& L = P.L[lo];
+  // PERSISTENT: one CTA per SM walks a contiguous range of tiles.  Tiles are ordered (layer, slab group, chunk),
+  // so consecutive tiles almost always share their (layer, slab group): the per-warp tables stay in shared memory
+  // across them and are folded into the fp64 arena only when that pair changes (the fold costs ~K x 2 x 1024
+  // global RED.F64 per CTA -- per tile it was a quarter of the kernel's time).
   const int K = P.K;
-  const int t = tile - P.tile_prefix[lo];
-  const int chunk = t / L.n_slab_groups, sg = t - chunk * L.n_slab_groups;
+  const int n_tiles = P.tile_prefix[P.n_layers];
+  const int t_first = static_cast<int>(static_cast<long long>(blockIdx.x) * n_tiles / gridDim.x);
+  const int t_last = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_tiles / gridDim.x);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int spc = L.spc, phases = kNhwcWarps / spc;
-  const int slab_local = warp % spc, phase = warp / spc;
-  const int c0 = (sg * spc + slab_local) * kNhwcSlab + lane * 4;
-  const bool lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside
-
   float* mine = tables + static_cast<size_t>(warp) * K * 256;
-  for (int i = lane; i < K * 64; i += 32) reinterpret_cast<float4*>(mine)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
+  const unsigned long long dropped = static_cast<unsigned long long>(K) * 0x0101010101010101ull;
 
+  struct Group {  // one pixel group in registers: every index below is a compile-time constant after unrolling
+    Raw x[G];
+    Raw d[BWD ? G : 1];
+    unsigned long long k[G / 8];  // packed keys; K = dropped
+  };
+
+  int layer = 0, cur_layer = -1, cur_sg = -1;
+  // state of the current (layer, slab group)
+  int spc = 1, phases = kNhwcWarps, phase = 0, c0 = 0, sg = 0;
+  bool lane_on = false, affine = false;
   f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
-  if (lane_on && (BWD || L.scale || L.shift)) {
-    float sc[4], sf[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sc[j] = L.scale ? L.scale[c0 + j] : 1.f;
-      sf[j] = L.shift ? L.shift[c0 + j] : 0.f;
-      if (L.centered) sf[j] = -sf[j] * sc[j];
-    }
-    sc01 = pack2(sc[0], sc[1]);
-    sc23 = pack2(sc[2], sc[3]);
-    sf01 = pack2(sf[0], sf[1]);
-    sf23 = pack2(sf[2], sf[3]);
-  }
-  const bool affine = BWD || L.scale || L.shift;
-
-  const int p_begin = chunk * L.px_per_chunk;
-  const int p_end = min(p_begin + L.px_per_chunk, L.n_px);
-  const int n_groups = (p_end - p_begin + G - 1) / G;
-  const size_t C = static_cast<size_t>(L.C);
-
   // open run: class (K = none) and the partial sums of this lane's 4 channels
   unsigned run_key = static_cast<unsigned>(K);
   f2 r1a = 0, r1b = 0, r2a = 0, r2b = 0;
+
   auto flush = [&]() {
     if (run_key < static_cast<unsigned>(K)) {
       float4* row = reinterpret_cast<float4*>(mine + run_key * 256) + lane;
@@ -538,6 +520,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
       row[32] = b;
     }
     r1a = r1b = r2a = r2b = 0;
+    run_key = static_cast<unsigned>(K);
   };
   auto add_px = [&](const Raw& xr, const Raw& dr) {
     f2 a, b;
@@ -556,100 +539,140 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
     r2a = fma2(a, a, r2a);
     r2b = fma2(b, b, r2b);
   };
-
-  struct Group {  // one pixel group in registers: every index below is a compile-time constant after unrolling
-    Raw x[G];
-    Raw d[BWD ? G : 1];
-    unsigned long long k[G / 8];  // packed keys; K = dropped
+  // per-warp tables -> fp64 arena (sum over the pixel phases of each slab; zero partials skipped), then re-zero
+  auto fold = [&]() {
+    flush();
+    __syncthreads();
+    const NhwcLayer& L = P.L[cur_layer];
+    const int width = spc * kNhwcSlab;
+    for (int idx = tid; idx < K * 2 * width; idx += kNhwcWarps * 32) {
+      const int cl = idx % width;
+      const int km = idx / width;  // k * 2 + moment
+      const int sl = cl / kNhwcSlab, within = cl - sl * kNhwcSlab;
+      const int c = (cur_sg * spc + sl) * kNhwcSlab + within;
+      if (c >= L.C) continue;
+      float sum = 0.f;
+      for (int ph = 0; ph < phases; ++ph) sum += tables[static_cast<size_t>(ph * spc + sl) * K * 256 + km * 128 + within];
+      if (sum == 0.f) continue;
+      double* dst = (km & 1) ? L.S2 : L.S1;
+      atomicAdd(&dst[static_cast<size_t>(km >> 1) * L.ld + c], static_cast<double>(sum));
+    }
+    __syncthreads();
   };
-  const unsigned long long dropped = static_cast<unsigned long long>(K) * 0x0101010101010101ull;
-  auto load_group = [&](int g, Group& B) {
-    const int p = p_begin + g * G;
-    if (p + G <= p_end) {
+
+  for (int tile = t_first; tile < t_last; ++tile) {
+    while (tile >= P.tile_prefix[layer + 1]) ++layer;
+    const NhwcLayer& L = P.L[layer];
+    const int t = tile - P.tile_prefix[layer];
+    sg = t / L.n_chunks;
+    const int chunk = t - sg * L.n_chunks;
+    if (layer != cur_layer || sg != cur_sg) {
+      if (cur_layer >= 0) fold();
+      for (int i = lane; i < K * 64; i += 32) reinterpret_cast<float4*>(mine)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      cur_layer = layer;
+      cur_sg = sg;
+      spc = L.spc;
+      phases = kNhwcWarps / spc;
+      phase = warp / spc;
+      c0 = (sg * spc + warp % spc) * kNhwcSlab + lane * 4;
+      lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside
+      affine = BWD || L.scale || L.shift;
+      sc01 = sc23 = pack2(1.f, 1.f);
+      sf01 = sf23 = 0;
+      if (lane_on && affine) {
+        float sc[4], sf[4];
 #pragma unroll
-      for (int q = 0; q < G / 8; ++q)
-        B.k[q] = L.keys ? __ldg(reinterpret_cast<const unsigned long long*>(L.keys + p) + q) : 0ull;
-      if (lane_on) {
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-          B.x[i] = V::load(L.x, (p + i) * C + c0);
-          if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
+        for (int j = 0; j < 4; ++j) {
+          sc[j] = L.scale ? L.scale[c0 + j] : 1.f;
+          sf[j] = L.shift ? L.shift[c0 + j] : 0.f;
+          if (L.centered) sf[j] = -sf[j] * sc[j];
         }
+        sc01 = pack2(sc[0], sc[1]);
+        sc23 = pack2(sc[2], sc[3]);
+        sf01 = pack2(sf[0], sf[1]);
+        sf23 = pack2(sf[2], sf[3]);
       }
-    } else {  // ragged tail of the chunk: pixel by pixel, missing pixels are "dropped"
+    }
+
+    const int p_begin = chunk * L.px_per_chunk;
+    const int p_end = min(p_begin + L.px_per_chunk, L.n_px);
+    const int n_groups = (p_end - p_begin + G - 1) / G;
+    const size_t C = static_cast<size_t>(L.C);
+
+    auto load_group = [&](int g, Group& B) {
+      const int p = p_begin + g * G;
+      if (p + G <= p_end) {
 #pragma unroll
-      for (int q = 0; q < G / 8; ++q) B.k[q] = dropped;
+        for (int q = 0; q < G / 8; ++q)
+          B.k[q] = L.keys ? __ldg(reinterpret_cast<const unsigned long long*>(L.keys + p) + q) : 0ull;
+        if (lane_on) {
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-        if (p + i < p_end) {
-          const unsigned long long k = L.keys ? L.keys[p + i] : 0;
-          const int sh = 8 * (i & 7);
-          B.k[i >> 3] = (B.k[i >> 3] & ~(0xffull << sh)) | (k << sh);
-          if (lane_on) {
+          for (int i = 0; i < G; ++i) {
             B.x[i] = V::load(L.x, (p + i) * C + c0);
             if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
           }
         }
-      }
-    }
-  };
-  auto consume = [&](const Group& B) {
-    const unsigned k0 = static_cast<unsigned>(B.k[0] & 0xffull);
-    bool uniform = true;
+      } else {  // ragged tail of the chunk: pixel by pixel, missing pixels are "dropped"
 #pragma unroll
-    for (int q = 0; q < G / 8; ++q) uniform = uniform && B.k[q] == k0 * 0x0101010101010101ull;
-    if (uniform) {  // the whole group continues (or opens) one run: branch-free accumulate
-      if (k0 != run_key) {
-        flush();
-        run_key = k0;
-      }
-      if (k0 < static_cast<unsigned>(K) && lane_on) {
+        for (int q = 0; q < G / 8; ++q) B.k[q] = dropped;
 #pragma unroll
-        for (int i = 0; i < G; ++i) add_px(B.x[i], B.d[BWD ? i : 0]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const unsigned k = static_cast<unsigned>(B.k[i >> 3] >> (8 * (i & 7))) & 0xffu;
-        if (k != run_key) {
-          flush();
-          run_key = k;
+        for (int i = 0; i < G; ++i) {
+          if (p + i < p_end) {
+            const unsigned long long k = L.keys ? L.keys[p + i] : 0;
+            const int sh = 8 * (i & 7);
+            B.k[i >> 3] = (B.k[i >> 3] & ~(0xffull << sh)) | (k << sh);
+            if (lane_on) {
+              B.x[i] = V::load(L.x, (p + i) * C + c0);
+              if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
+            }
+          }
         }
-        if (k < static_cast<unsigned>(K) && lane_on) add_px(B.x[i], B.d[BWD ? i : 0]);
       }
+    };
+    auto consume = [&](const Group& B) {
+      const unsigned k0 = static_cast<unsigned>(B.k[0] & 0xffull);
+      bool uniform = true;
+#pragma unroll
+      for (int q = 0; q < G / 8; ++q) uniform = uniform && B.k[q] == k0 * 0x0101010101010101ull;
+      if (uniform) {  // the whole group continues (or opens) one run: branch-free accumulate
+        if (k0 != run_key) {
+          flush();
+          run_key = k0;
+        }
+        if (k0 < static_cast<unsigned>(K) && lane_on) {
+#pragma unroll
+          for (int i = 0; i < G; ++i) add_px(B.x[i], B.d[BWD ? i : 0]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const unsigned k = static_cast<unsigned>(B.k[i >> 3] >> (8 * (i & 7))) & 0xffu;
+          if (k != run_key) {
+            flush();
+            run_key = k;
+          }
+          if (k < static_cast<unsigned>(K) && lane_on) add_px(B.x[i], B.d[BWD ? i : 0]);
+        }
+      }
+    };
+
+    // groups of this warp: phase, phase + phases, ...; the next group's loads are in flight while one is consumed
+    Group A, B;
+    int g = phase;
+    if (g < n_groups) load_group(g, A);
+    while (g < n_groups) {
+      if (g + phases < n_groups) load_group(g + phases, B);
+      consume(A);
+      g += phases;
+      if (g >= n_groups) break;
+      if (g + phases < n_groups) load_group(g + phases, A);
+      consume(B);
+      g += phases;
     }
-  };
-
-  // groups of this warp: phase, phase + phases, ...; the next group's loads are in flight while one is consumed
-  Group A, B;
-  int g = phase;
-  if (g < n_groups) load_group(g, A);
-  while (g < n_groups) {
-    if (g + phases < n_groups) load_group(g + phases, B);
-    consume(A);
-    g += phases;
-    if (g >= n_groups) break;
-    if (g + phases < n_groups) load_group(g + phases, A);
-    consume(B);
-    g += phases;
+    flush();  // bounds the length of an fp32 run to one chunk
   }
-  flush();
-  __syncthreads();
-
-  // ---- per-warp tables -> fp64 arena (sum over the pixel phases of each slab; zero partials skipped) ----------
-  const int width = spc * kNhwcSlab;
-  for (int idx = tid; idx < K * 2 * width; idx += kNhwcWarps * 32) {
-    const int cl = idx % width;
-    const int km = idx / width;  // k * 2 + moment
-    const int sl = cl / kNhwcSlab, within = cl - sl * kNhwcSlab;
-    const int c = (sg * spc + sl) * kNhwcSlab + within;
-    if (c >= L.C) continue;
-    float s = 0.f;
-    for (int ph = 0; ph < phases; ++ph) s += tables[static_cast<size_t>(ph * spc + sl) * K * 256 + km * 128 + within];
-    if (s == 0.f) continue;
-    double* dst = (km & 1) ? L.S2 : L.S1;
-    atomicAdd(&dst[static_cast<size_t>(km >> 1) * L.ld + c], static_cast<double>(s));
-  }
+  if (cur_layer >= 0) fold();
 }
 
 // Generic path: any extent / alignment / layout (tiny 1x1..6x6 maps, odd crops, NHWC).  One
@@ -859,7 +882,7 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
   auto kern = class_stats_nhwc_kernel<T, BWD, MAXL>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
-  kern<<<n_tiles, kNhwcWarps * 32, smem, stream>>>(P);
+  kern<<<std::min(n_tiles, kNumSMs), kNhwcWarps * 32, smem, stream>>>(P);  // persistent: one CTA per SM
   return finish_launch("class_stats_nhwc");
 }
 
@@ -969,9 +992,8 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
     }
   }
   if (n_nhwc > 0) {
-    // ~1 MB of x per CTA (one CTA per SM), halved while the call cannot fill ~6 waves
-    long long target = 1 << 20;
-    while (target > (64 << 10) && nhwc_bytes / target < 6LL * kNumSMs) target >>= 1;
+    // persistent CTAs (one per SM) each walk ~8 tiles: ~1/8 of an SM's share of the call per tile, 128 KB .. 2 MB
+    long long target = std::min<long long>(2 << 20, std::max<long long>(128 << 10, nhwc_bytes / (8LL * kNumSMs)));
     for (int first = 0; first < n_nhwc;) {
       const int m = std::min(n_nhwc - first, kNhwcBigGroup);
       int rc;
