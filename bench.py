@@ -231,7 +231,7 @@ def run_b200_arm(args, c):
     tf32 = args.conv_precision == "tf32"
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("DCFP_BENCH_CUDNN_BENCHMARK", "1") == "1"
 
     K, W, mb = args.steps, args.warmup, args.micro_batch
     model = build_segnet(c["arch"], c["backbone"], c["num_classes"], seed=0).to(dev)
@@ -278,6 +278,7 @@ def run_b200_arm(args, c):
     barrier()
     sc.k1_events.clear()
     launches0 = ops.launch_count()
+    mem0 = torch.cuda.memory_stats(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     barrier()
@@ -286,10 +287,16 @@ def run_b200_arm(args, c):
     nvtx_range = torch.cuda.nvtx.range_start("timed")
     e0.record()
     marks = [e0]
+    debug = os.environ.get("DCFP_BENCH_DEBUG") == "1"
+    dbg = []
     for s in range(W, W + K):
         run.step(*resident[s], mb_index=s * world + rank)
         marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record()
+        if debug:
+            m = torch.cuda.memory_stats(dev)
+            dbg.append((m.get("num_device_alloc", 0), m.get("num_device_free", 0), m.get("num_alloc_retries", 0),
+                        round(m.get("reserved_bytes.all.current", 0) / 1e9, 2), round(time.time() - t_wall0, 3)))
     e1.record()
     torch.cuda.nvtx.range_end(nvtx_range)
     barrier()
@@ -297,6 +304,11 @@ def run_b200_arm(args, c):
     step_ms = [round(a.elapsed_time(b), 3) for a, b in zip(marks[:-1], marks[1:])]
     ms_a = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.launch_count() - launches0
+    mem1 = torch.cuda.memory_stats(dev)
+    alloc = {"cudaMalloc_calls_in_timed_region": mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0),
+             "cudaFree_calls_in_timed_region": mem1.get("num_device_free", 0) - mem0.get("num_device_free", 0),
+             "alloc_retries_in_timed_region": mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0),
+             "debug": dbg, "reserved_gb": mem1.get("reserved_bytes.all.current", 0) / 1e9, "allocated_peak_gb": mem1.get("allocated_bytes.all.peak", 0) / 1e9}
     k1_ms, k1_bytes, k1_launches = sc.k1_time_ms()
     share_a = k1_ms / max(e0.elapsed_time(e1), 1e-9)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
@@ -378,7 +390,7 @@ def run_b200_arm(args, c):
                                        "fold -> all-reduce(dgamma)/N -> EIC update; no optimizer step",
                            "l2": "per-step feature maps (%.1f GB read by K1) exceed the 126 MB L2; no explicit flush" % (k1_bytes / K / 1e9),
                            "layout": args.layout, "k1_flush_mib": args.flush_mb, "priming_steps": args.prime, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
-                "step_ms": step_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K,sumC] fp64 totals + counts at the end of the pass"}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -174,22 +174,29 @@ class ClassStatsScorer:
                 return
             if not output.requires_grad:
                 return
-            node = output.grad_fn
             training = module.training or module.running_mean is None
+            # batch statistics autograd's BN node saved (CudnnBatchNormBackward0 / NativeBatchNormBackward0: result1 =
+            # mean, result2 = invstd).  Read them NOW: capturing the node in the gradient hook below would close a
+            # reference cycle node -> hook -> closure -> node that Python's GC cannot see, leaking x every step.
+            mean = invstd = None
+            if training:
+                node = output.grad_fn
+                mean = getattr(node, "_saved_result1", None)
+                invstd = getattr(node, "_saved_result2", None)
+                del node
+                if mean is None or invstd is None or mean.numel() != x.shape[1] or mean.dtype != torch.float32:
+                    mean = invstd = None
 
-            def on_grad(dy):
+            def on_grad(dy, mean=mean, invstd=invstd):
                 with torch.no_grad():
                     xd = x.detach()
-                    if training:
-                        mean = getattr(node, "_saved_result1", None)
-                        invstd = getattr(node, "_saved_result2", None)
-                        if mean is None or invstd is None or mean.numel() != xd.shape[1] or mean.dtype != torch.float32:
-                            # BN implementation that saves nothing usable: recompute the batch statistics
-                            var, mean = torch.var_mean(xd.float(), dim=(0, 2, 3), unbiased=False)
-                            invstd = torch.rsqrt(var + module.eps)
-                    else:
+                    if not training:
                         mean = module.running_mean.float()
                         invstd = torch.rsqrt(module.running_var.float() + module.eps)
+                    elif mean is None:
+                        # BN implementation that saves nothing usable: recompute the batch statistics
+                        var, mean = torch.var_mean(xd.float(), dim=(0, 2, 3), unbiased=False)
+                        invstd = torch.rsqrt(var + module.eps)
                     # K1 wants x and dy in ONE layout: follow x (the tensor autograd saved, never copied)
                     if xd.is_contiguous():
                         g = dy.contiguous()

@@ -23,7 +23,8 @@ def keys_for(shapes):
     return out
 shapes = [(1024, 64, 128 // S)] * 5 + [(256, 64, 128 // S)] * 12 + [(512, 64, 128 // S)] * 3 + [(2048, 64, 128 // S)] + \
     [(256, 128, 256 // S)] + [(64, 256, 512 // S)]
-xs = [torch.randn(2, c, h, w, device=dev).to(dtype) for c, h, w in shapes]
+fmt = torch.channels_last if os.environ.get("LAYOUT", "nchw") == "nhwc" else torch.contiguous_format
+xs = [torch.randn(2, c, h, w, device=dev).to(dtype).contiguous(memory_format=fmt) for c, h, w in shapes]
 dys = [torch.randn_like(x) for x in xs] if bwd else None
 sc = [torch.ones(c, device=dev) for c, _, _ in shapes] if bwd else None
 sf = [torch.zeros(c, device=dev) for c, _, _ in shapes] if bwd else None

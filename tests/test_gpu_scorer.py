@@ -169,3 +169,34 @@ def test_dcfp_pruning_step_api_matches_scorer(native):
         bad += int((~_close(a, b, 5e-4)).sum())
     assert bad <= 5, "%d channels differ (sign-gate flips at |dgamma| ~ 0 are the only legitimate ones)" % bad
     run.close()
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_steady_state_memory_and_channels_last_model(native, channels_last):
+    """No per-step growth of device memory (the gradient hooks must not close a reference cycle through the autograd
+    node), and a channels_last model -- NHWC feature maps, K1's NHWC path -- gives the same dgamma as autograd."""
+    from dcfp_b200.scorer import CalibrationRun
+    model = _setup()
+    x, y = _batch([0, 1], valid_only=True)
+    x, y = x.to(DEV), y.to(DEV)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    run = CalibrationRun(model, K, r=0.999, seed=3)
+    used = []
+    for s in range(4):
+        run.step(x, y, mb_index=s)
+        torch.cuda.synchronize()
+        used.append(torch.cuda.memory_allocated())
+    assert used[3] == used[2] == used[1], used
+    sc = run.scorer
+    S1 = sc.totals[0].sum(0).cpu().numpy() / 4  # four identical steps up to dropout -> compare the last step instead
+    dgamma_last = torch.cat([m.weight.grad.detach().reshape(-1) for _, m in sc.layers]).cpu().numpy()
+    run.close()
+    run = CalibrationRun(model, K, r=0.999, seed=3)
+    run.step(x, y, mb_index=3)
+    S1 = run.scorer.totals[0].sum(0).cpu().numpy()
+    g = torch.cat([m.weight.grad.detach().reshape(-1) for _, m in run.scorer.layers]).cpu().numpy()
+    ok = _close(S1, g)
+    assert ok.mean() > 0.999, "%d channels off" % (~ok).sum()
+    run.close()
