@@ -413,14 +413,17 @@ __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
 // channels the class key is warp-uniform by construction and the loads are coalesced as they are -- no
 // shared-memory transposition, no TMA staging.  A warp streams the pixels of its [128-channel slab] with
 // 128-bit (fp32) / 64-bit (bf16) loads, software-pipelined one pixel group ahead, and keeps the OPEN CLASS RUN
-// (sum, sum of squares of its 4 channels) in registers; its private [K][2][128] fp32 table in shared memory is
-// touched only when the class changes.  A CTA's 8 warps cover `spc` adjacent slabs x 8/spc pixel phases, so a
-// CTA reads one fully contiguous range of memory.  cuDNN's tensor-core convolutions are NHWC-native: running
-// the feature-map producer in channels_last removes its layout transposes (measured 52 -> 35 ms per c2 step),
-// which is why this is the layout bench.py scores.
-constexpr int kNhwcWarps = 8;
-constexpr int kNhwcSlab = 128;      // channels per warp row: 32 lanes x 4
-constexpr int kNhwcMaxK = 27;       // 8 warps x K x 1 KB of tables must fit in 227 KB
+// (sum, sum of squares of its 4 channels) in registers.  A closed run goes to the warp's private SLOT CACHE in
+// shared memory: 8 rows of [2][128] fp32, tagged with the class they hold (an 8 x 8-bit tag word in a register;
+// labels are spatially coherent, so a warp meets few classes at a time); a ninth class evicts a row to the fp64
+// arena.  8 KB per warp for ANY K <= 255 -- 16 warps per SM, no table sized by K, no shared atomics, and no
+// CTA-wide barrier anywhere in the kernel.  The kernel is PERSISTENT (one CTA per SM walks a contiguous range of
+// tiles ordered (layer, slab group, chunk)); rows are folded into the arena only when the (layer, slab group)
+// changes.  cuDNN's tensor-core convolutions are NHWC-native: running the feature-map producer in channels_last
+// removes its layout transposes (measured 52 -> 36 ms per c2 step), which is why bench.py scores this layout.
+constexpr int kNhwcWarps = 16;
+constexpr int kNhwcSlab = 128;   // channels per warp row: 32 lanes x 4
+constexpr int kNhwcSlots = 8;    // class rows per warp
 
 struct NhwcLayer {
   const void* x;
@@ -432,9 +435,9 @@ struct NhwcLayer {
   double* S2;
   int32_t C, ld, centered;
   int32_t n_px;           // N * HW
-  int32_t spc;            // slabs per CTA: 1, 2, 4 or 8
+  int32_t spc;            // slabs per CTA: 1, 2, 4, 8 or 16
   int32_t n_slab_groups;  // ceil(ceil(C / 128) / spc)
-  int32_t px_per_chunk;   // multiple of 16 * (8 / spc)
+  int32_t px_per_chunk;   // multiple of G * (16 / spc)
   int32_t n_chunks;
 };
 template <int MAXL>
@@ -451,13 +454,19 @@ template <typename T>
 struct Vec4;
 template <>
 struct Vec4<float> {
-  using Raw = uint4;
+  struct Raw {
+    f2 a, b;
+  };
   __device__ static __forceinline__ Raw load(const void* base, size_t elem) {
-    return ldg_stream128(static_cast<const float*>(base) + elem);
+    Raw v;  // two 64-bit registers = two f32x2 operands, no repacking
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];"
+                 : "=l"(v.a), "=l"(v.b)
+                 : "l"(static_cast<const float*>(base) + elem));
+    return v;
   }
   __device__ static __forceinline__ void unpack(const Raw& r, f2& a, f2& b) {
-    a = static_cast<f2>(r.x) | (static_cast<f2>(r.y) << 32);
-    b = static_cast<f2>(r.z) | (static_cast<f2>(r.w) << 32);
+    a = r.a;
+    b = r.b;
   }
 };
 template <>
@@ -476,53 +485,90 @@ struct Vec4<__nv_bfloat16> {
   }
 };
 
+template <typename T, bool BWD>
+struct NhwcGroupPx {  // pixels per group: all loads of a group are in flight together (4 KB per warp)
+  static constexpr int value = (sizeof(T) == 4 ? 8 : 16) / (BWD ? 2 : 1);
+};
+
 template <typename T, bool BWD, int MAXL>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL> P) {
-  constexpr int G = BWD ? 8 : 16;  // pixels per group (one packed key vector), all loads of a group in flight
+  constexpr int G = NhwcGroupPx<T, BWD>::value;
+  constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
   using V = Vec4<T>;
   using Raw = typename V::Raw;
-  extern __shared__ __align__(16) float tables[];  // [warp][K][2][128]
+  extern __shared__ __align__(16) float slots[];  // [warp][slot][2][128]
 
-  // PERSISTENT: one CTA per SM walks a contiguous range of tiles.  Tiles are ordered (layer, slab group, chunk),
-  // so consecutive tiles almost always share their (layer, slab group): the per-warp tables stay in shared memory
-  // across them and are folded into the fp64 arena only when that pair changes (the fold costs ~K x 2 x 1024
-  // global RED.F64 per CTA -- per tile it was a quarter of the kernel's time).
-  const int K = P.K;
+  const unsigned K = static_cast<unsigned>(P.K);
   const int n_tiles = P.tile_prefix[P.n_layers];
   const int t_first = static_cast<int>(static_cast<long long>(blockIdx.x) * n_tiles / gridDim.x);
   const int t_last = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_tiles / gridDim.x);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* mine = tables + static_cast<size_t>(warp) * K * 256;
-  const unsigned long long dropped = static_cast<unsigned long long>(K) * 0x0101010101010101ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* const mine = reinterpret_cast<float4*>(slots + static_cast<size_t>(warp) * kNhwcSlots * 256) + lane;
+  const unsigned dropped = K * 0x01010101u;
+  const bool direct = K <= static_cast<unsigned>(kNhwcSlots);  // slot == class, no tags
 
   struct Group {  // one pixel group in registers: every index below is a compile-time constant after unrolling
     Raw x[G];
     Raw d[BWD ? G : 1];
-    unsigned long long k[G / 8];  // packed keys; K = dropped
+    unsigned k[Q];  // packed keys; K = dropped
   };
 
   int layer = 0, cur_layer = -1, cur_sg = -1;
-  // state of the current (layer, slab group)
-  int spc = 1, phases = kNhwcWarps, phase = 0, c0 = 0, sg = 0;
+  int phases = kNhwcWarps, phase = 0, c0 = 0;
   bool lane_on = false, affine = false;
+  double* out1 = nullptr;  // &S1[c0], &S2[c0] of the current layer
+  double* out2 = nullptr;
+  size_t ld = 0;
   f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
-  // open run: class (K = none) and the partial sums of this lane's 4 channels
-  unsigned run_key = static_cast<unsigned>(K);
+  // open run: class (K = none / dropped) and the partial sums of this lane's 4 channels
+  unsigned run_key = K;
   f2 r1a = 0, r1b = 0, r2a = 0, r2b = 0;
+  // slot cache: class held by each row (0xff = free), round-robin victim
+  unsigned long long tags = ~0ull;
+  int victim = 0;
 
-  auto flush = [&]() {
-    if (run_key < static_cast<unsigned>(K)) {
-      float4* row = reinterpret_cast<float4*>(mine + run_key * 256) + lane;
-      float4 a = row[0], b = row[32];
+  auto row_to_arena = [&](int slot, unsigned cls) {  // fp32 row -> fp64 arena, row zeroed
+    const float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
+    if (lane_on) {
+      double* d1 = out1 + cls * ld;
+      double* d2 = out2 + cls * ld;
+      if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));
+      if (a.y != 0.f) atomicAdd(d1 + 1, static_cast<double>(a.y));
+      if (a.z != 0.f) atomicAdd(d1 + 2, static_cast<double>(a.z));
+      if (a.w != 0.f) atomicAdd(d1 + 3, static_cast<double>(a.w));
+      if (b.x != 0.f) atomicAdd(d2 + 0, static_cast<double>(b.x));
+      if (b.y != 0.f) atomicAdd(d2 + 1, static_cast<double>(b.y));
+      if (b.z != 0.f) atomicAdd(d2 + 2, static_cast<double>(b.z));
+      if (b.w != 0.f) atomicAdd(d2 + 3, static_cast<double>(b.w));
+    }
+    mine[slot * 64] = make_float4(0.f, 0.f, 0.f, 0.f);
+    mine[slot * 64 + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto slot_of = [&](unsigned cls) -> int {  // warp-uniform
+    if (direct) return static_cast<int>(cls);
+    const unsigned long long x = tags ^ (0x0101010101010101ull * cls);
+    const unsigned long long z = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;  // lowest hit is exact
+    if (z) return (__ffsll(static_cast<long long>(z)) - 1) >> 3;
+    const int slot = victim;
+    victim = (victim + 1) & (kNhwcSlots - 1);
+    const unsigned old = static_cast<unsigned>(tags >> (8 * slot)) & 0xffu;
+    if (old != 0xffu) row_to_arena(slot, old);
+    tags = (tags & ~(0xffull << (8 * slot))) | (static_cast<unsigned long long>(cls) << (8 * slot));
+    return slot;
+  };
+  auto close_run = [&](unsigned next_key) {
+    if (run_key < K) {
+      const int slot = slot_of(run_key);
+      float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
       a.x += lo2(r1a); a.y += hi2(r1a); a.z += lo2(r1b); a.w += hi2(r1b);
       b.x += lo2(r2a); b.y += hi2(r2a); b.z += lo2(r2b); b.w += hi2(r2b);
-      row[0] = a;
-      row[32] = b;
+      mine[slot * 64] = a;
+      mine[slot * 64 + 32] = b;
     }
     r1a = r1b = r2a = r2b = 0;
-    run_key = static_cast<unsigned>(K);
+    run_key = next_key;
   };
-  auto add_px = [&](const Raw& xr, const Raw& dr) {
+  auto add_px = [&](const Raw& xr, const Raw& dr) {  // unconditional: a dropped run is discarded when it closes
     f2 a, b;
     V::unpack(xr, a, b);
     if (BWD) {
@@ -539,44 +585,51 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
     r2a = fma2(a, a, r2a);
     r2b = fma2(b, b, r2b);
   };
-  // per-warp tables -> fp64 arena (sum over the pixel phases of each slab; zero partials skipped), then re-zero
-  auto fold = [&]() {
-    flush();
-    __syncthreads();
-    const NhwcLayer& L = P.L[cur_layer];
-    const int width = spc * kNhwcSlab;
-    for (int idx = tid; idx < K * 2 * width; idx += kNhwcWarps * 32) {
-      const int cl = idx % width;
-      const int km = idx / width;  // k * 2 + moment
-      const int sl = cl / kNhwcSlab, within = cl - sl * kNhwcSlab;
-      const int c = (cur_sg * spc + sl) * kNhwcSlab + within;
-      if (c >= L.C) continue;
-      float sum = 0.f;
-      for (int ph = 0; ph < phases; ++ph) sum += tables[static_cast<size_t>(ph * spc + sl) * K * 256 + km * 128 + within];
-      if (sum == 0.f) continue;
-      double* dst = (km & 1) ? L.S2 : L.S1;
-      atomicAdd(&dst[static_cast<size_t>(km >> 1) * L.ld + c], static_cast<double>(sum));
+  auto fold = [&]() {  // every row of this warp -> arena (end of a (layer, slab group))
+    close_run(K);
+    if (direct) {
+      for (unsigned k = 0; k < K; ++k) row_to_arena(static_cast<int>(k), k);
+    } else {
+      for (int slot = 0; slot < kNhwcSlots; ++slot) {
+        const unsigned cls = static_cast<unsigned>(tags >> (8 * slot)) & 0xffu;
+        if (cls != 0xffu) row_to_arena(slot, cls);
+      }
+      tags = ~0ull;
+      victim = 0;
     }
-    __syncthreads();
   };
+
+  for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  Group A, B;
+#pragma unroll
+  for (int i = 0; i < G; ++i) {  // lanes beyond C never load: keep their registers defined
+    A.x[i] = Raw{};
+    B.x[i] = Raw{};
+    if (BWD) {
+      A.d[i] = Raw{};
+      B.d[i] = Raw{};
+    }
+  }
 
   for (int tile = t_first; tile < t_last; ++tile) {
     while (tile >= P.tile_prefix[layer + 1]) ++layer;
     const NhwcLayer& L = P.L[layer];
     const int t = tile - P.tile_prefix[layer];
-    sg = t / L.n_chunks;
+    const int sg = t / L.n_chunks;
     const int chunk = t - sg * L.n_chunks;
     if (layer != cur_layer || sg != cur_sg) {
       if (cur_layer >= 0) fold();
-      for (int i = lane; i < K * 64; i += 32) reinterpret_cast<float4*>(mine)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncwarp();
       cur_layer = layer;
       cur_sg = sg;
-      spc = L.spc;
+      const int spc = L.spc;
       phases = kNhwcWarps / spc;
       phase = warp / spc;
       c0 = (sg * spc + warp % spc) * kNhwcSlab + lane * 4;
       lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside
+      ld = static_cast<size_t>(L.ld);
+      out1 = L.S1 + c0;
+      out2 = L.S2 + c0;
       affine = BWD || L.scale || L.shift;
       sc01 = sc23 = pack2(1.f, 1.f);
       sf01 = sf23 = 0;
@@ -600,65 +653,54 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
     const int n_groups = (p_end - p_begin + G - 1) / G;
     const size_t C = static_cast<size_t>(L.C);
 
-    auto load_group = [&](int g, Group& B) {
+    auto load_group = [&](int g, Group& D) {
       const int p = p_begin + g * G;
       if (p + G <= p_end) {
 #pragma unroll
-        for (int q = 0; q < G / 8; ++q)
-          B.k[q] = L.keys ? __ldg(reinterpret_cast<const unsigned long long*>(L.keys + p) + q) : 0ull;
+        for (int q = 0; q < Q; ++q) D.k[q] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + p) + q) : 0u;
         if (lane_on) {
 #pragma unroll
           for (int i = 0; i < G; ++i) {
-            B.x[i] = V::load(L.x, (p + i) * C + c0);
-            if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
+            D.x[i] = V::load(L.x, (p + i) * C + c0);
+            if (BWD) D.d[i] = V::load(L.dy, (p + i) * C + c0);
           }
         }
       } else {  // ragged tail of the chunk: pixel by pixel, missing pixels are "dropped"
 #pragma unroll
-        for (int q = 0; q < G / 8; ++q) B.k[q] = dropped;
+        for (int q = 0; q < Q; ++q) D.k[q] = dropped;
 #pragma unroll
         for (int i = 0; i < G; ++i) {
           if (p + i < p_end) {
-            const unsigned long long k = L.keys ? L.keys[p + i] : 0;
-            const int sh = 8 * (i & 7);
-            B.k[i >> 3] = (B.k[i >> 3] & ~(0xffull << sh)) | (k << sh);
+            const unsigned k = L.keys ? L.keys[p + i] : 0u;
+            const int sh = 8 * (i & 3);
+            D.k[i >> 2] = (D.k[i >> 2] & ~(0xffu << sh)) | (k << sh);
             if (lane_on) {
-              B.x[i] = V::load(L.x, (p + i) * C + c0);
-              if (BWD) B.d[i] = V::load(L.dy, (p + i) * C + c0);
+              D.x[i] = V::load(L.x, (p + i) * C + c0);
+              if (BWD) D.d[i] = V::load(L.dy, (p + i) * C + c0);
             }
           }
         }
       }
     };
-    auto consume = [&](const Group& B) {
-      const unsigned k0 = static_cast<unsigned>(B.k[0] & 0xffull);
-      bool uniform = true;
+    auto consume = [&](const Group& D) {
 #pragma unroll
-      for (int q = 0; q < G / 8; ++q) uniform = uniform && B.k[q] == k0 * 0x0101010101010101ull;
-      if (uniform) {  // the whole group continues (or opens) one run: branch-free accumulate
-        if (k0 != run_key) {
-          flush();
-          run_key = k0;
-        }
-        if (k0 < static_cast<unsigned>(K) && lane_on) {
+      for (int q = 0; q < Q; ++q) {
+        const unsigned w = D.k[q];
+        if (w == run_key * 0x01010101u) {  // the quad continues the open run: branch-free
 #pragma unroll
-          for (int i = 0; i < G; ++i) add_px(B.x[i], B.d[BWD ? i : 0]);
-        }
-      } else {
+          for (int e = 0; e < 4; ++e) add_px(D.x[4 * q + e], D.d[BWD ? 4 * q + e : 0]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-          const unsigned k = static_cast<unsigned>(B.k[i >> 3] >> (8 * (i & 7))) & 0xffu;
-          if (k != run_key) {
-            flush();
-            run_key = k;
+          for (int e = 0; e < 4; ++e) {
+            const unsigned k = (w >> (8 * e)) & 0xffu;
+            if (k != run_key) close_run(k);
+            add_px(D.x[4 * q + e], D.d[BWD ? 4 * q + e : 0]);
           }
-          if (k < static_cast<unsigned>(K) && lane_on) add_px(B.x[i], B.d[BWD ? i : 0]);
         }
       }
     };
 
     // groups of this warp: phase, phase + phases, ...; the next group's loads are in flight while one is consumed
-    Group A, B;
     int g = phase;
     if (g < n_groups) load_group(g, A);
     while (g < n_groups) {
@@ -670,7 +712,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
       consume(B);
       g += phases;
     }
-    flush();  // bounds the length of an fp32 run to one chunk
+    close_run(K);  // bounds the length of an fp32 run to one chunk
   }
   if (cur_layer >= 0) fold();
 }
@@ -829,13 +871,13 @@ bool tiled_ok(const dcfp_layer_desc& d) {
 
 // the NHWC fast path: whole 4-channel vectors, 16-B aligned rows, per-warp tables that fit in shared memory
 bool nhwc_ok(const dcfp_layer_desc& d) {
-  if (d.layout != DCFP_NHWC || d.K > kNhwcMaxK) return false;
+  if (d.layout != DCFP_NHWC) return false;
   const size_t es = d.dtype == DCFP_F32 ? 4 : 2;
   if (d.C % 4 != 0 || (static_cast<size_t>(d.C) * es) % (4 * es) != 0) return false;
   const uintptr_t al = 4 * es;  // one lane's vector
   if (reinterpret_cast<uintptr_t>(d.x) % al != 0) return false;
   if (d.dy && reinterpret_cast<uintptr_t>(d.dy) % al != 0) return false;
-  if (d.keys && reinterpret_cast<uintptr_t>(d.keys) % 16 != 0) return false;
+  if (d.keys && reinterpret_cast<uintptr_t>(d.keys) % 4 != 0) return false;
   if (static_cast<long long>(d.N) * d.h * d.w < 64) return false;  // tiny pooled maps: generic
   return true;
 }
@@ -866,7 +908,7 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
     L.spc = spc;
     L.n_slab_groups = (n_slabs + spc - 1) / spc;
-    const int gran = (BWD ? 8 : 16) * (kNhwcWarps / spc);  // every phase gets whole pixel groups
+    const int gran = NhwcGroupPx<T, BWD>::value * (kNhwcWarps / spc);  // every phase gets whole pixel groups
     const long long row_bytes = static_cast<long long>(std::min(d.C, spc * kNhwcSlab)) * sizeof(T);
     long long px = std::max<long long>(target_bytes / row_bytes, gran);
     px = (px + gran - 1) / gran * gran;
@@ -878,7 +920,7 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
   }
   const int n_tiles = P.tile_prefix[n];
   if (n_tiles == 0) return 0;
-  const size_t smem = static_cast<size_t>(kNhwcWarps) * K * 256 * sizeof(float);
+  const size_t smem = static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float);
   auto kern = class_stats_nhwc_kernel<T, BWD, MAXL>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;

@@ -270,3 +270,13 @@ def test_channels_last_invstd_mean_mode_and_no_keys(native):
         ops.class_stats(x.to(dev), None, 1, T1, T2)
         assert ((T1[0].cpu() - x.double().sum((0, 2, 3))).abs() <= RTOL * x.double().abs().sum((0, 2, 3))).all()
         assert ((T2[0].cpu() - (x.double() ** 2).sum((0, 2, 3))).abs() <= RTOL * (x.double() ** 2).sum((0, 2, 3))).all()
+
+
+@pytest.mark.parametrize("K", [5, 19, 171])
+def test_channels_last_iid_labels_thrash_the_slot_cache(native, K):
+    """i.i.d. labels: every pixel opens a new run and (K > 8) almost every run evicts a row of the per-warp slot cache."""
+    from dcfp_b200 import ops
+    N, C, h, w = 2, 192, 24, 40
+    x = torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(K)).contiguous(memory_format=torch.channels_last)
+    label = _labels(N, h, w, K, torch.uint8, seed=K + 1, blob=False)
+    _check(ops, x, label, K)
