@@ -410,24 +410,25 @@ __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
 
 // ---- channels_last (NHWC) path ---------------------------------------------------------------------
 // x[n][p][c] with C contiguous: every pixel has ONE class for all its channels, so with lane = 4 consecutive
-// channels the class key is warp-uniform by construction and the loads are coalesced as they are -- no
-// shared-memory transposition, no TMA staging.  A warp streams the pixels of its [128-channel slab] with
-// 128-bit (fp32) / 64-bit (bf16) loads, software-pipelined one pixel group ahead, and keeps the OPEN CLASS RUN
-// (sum, sum of squares of its 4 channels) in registers.  A closed run goes to the warp's private SLOT CACHE in
-// shared memory: 8 rows of [2][128] fp32, tagged with the class they hold (an 8 x 8-bit tag word in a register;
-// labels are spatially coherent, so a warp meets few classes at a time); a ninth class evicts a row to the fp64
-// arena.  8 KB per warp for ANY K <= 255 -- 16 warps per SM, no table sized by K, no shared atomics, and no
-// CTA-wide barrier anywhere in the kernel.  The kernel is PERSISTENT (one CTA per SM walks a contiguous range of
-// tiles ordered (layer, slab group, chunk)); rows are folded into the arena only when the (layer, slab group)
-// changes.  cuDNN's tensor-core convolutions are NHWC-native: running the feature-map producer in channels_last
-// removes its layout transposes (measured 52 -> 36 ms per c2 step), which is why bench.py scores this layout.
-constexpr int kNhwcWarps = 16;
-constexpr int kNhwcSlab = 128;   // channels per warp row: 32 lanes x 4
-constexpr int kNhwcSlots = 8;    // class rows per warp
+// channels the class key is warp-uniform by construction and a pixel's [128-channel slab] is read straight out of
+// a TMA-staged box with one conflict-free LDS per lane -- no transposition.  Each warp owns a slab and a pixel
+// phase and runs a private multi-stage pipeline of [G pixels x 128 channels] tensor-tile copies (cp.async.bulk.
+// tensor.2d, mbarrier completion, evict-first): the bytes in flight live in shared memory, not in registers or
+// L1 miss queues (a register-staged LDG version of this kernel stalled at 56 % of the roofline with the same
+// nominal bytes in flight).  The OPEN CLASS RUN (sum, sum of squares of the lane's 4 channels) stays in registers;
+// a closed run goes to the warp's private SLOT CACHE: 8 rows of [2][128] fp32 tagged with the class they hold (an
+// 8 x 8-bit tag word in a register; labels are spatially coherent, so a warp meets few classes at a time); a
+// ninth class evicts a row to the fp64 arena.  8 KB per warp for ANY K <= 255: no table sized by K, no shared
+// atomics, no CTA-wide barrier in the main loop.  The kernel is PERSISTENT (one CTA per SM walks a contiguous
+// range of tiles ordered (layer, slab group, chunk)); rows are folded into the arena only when the (layer, slab
+// group) changes.  cuDNN's tensor-core convolutions are NHWC-native: running the feature-map producer in
+// channels_last removes its layout transposes (measured 52 -> 36 ms per c2 step) -- the layout bench.py scores.
+constexpr int kNhwcWarps = 8;
+constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
+constexpr int kNhwcSlots = 8;        // class rows per warp
+constexpr int kNhwcBoxBytes = 4096;  // [G px][128 ch]: G = 8 (fp32) / 16 (bf16)
 
 struct NhwcLayer {
-  const void* x;
-  const void* dy;
   const uint8_t* keys;  // [N*HW]
   const float* scale;
   const float* shift;
@@ -435,68 +436,63 @@ struct NhwcLayer {
   double* S2;
   int32_t C, ld, centered;
   int32_t n_px;           // N * HW
-  int32_t spc;            // slabs per CTA: 1, 2, 4, 8 or 16
+  int32_t spc;            // slabs per CTA: 1, 2, 4 or 8
   int32_t n_slab_groups;  // ceil(ceil(C / 128) / spc)
-  int32_t px_per_chunk;   // multiple of G * (16 / spc)
+  int32_t px_per_chunk;   // multiple of G * (8 / spc)
   int32_t n_chunks;
 };
-template <int MAXL>
+template <int MAXL, int TENS>
 struct NhwcParams {
+  alignas(64) CUtensorMap maps[MAXL * TENS];  // [layer][x, dy]: [n_px rows][C cols], box [G][128]
   NhwcLayer L[MAXL];
   int32_t tile_prefix[MAXL + 1];
   int32_t n_layers;
   int32_t K;
 };
-constexpr int kNhwcBigGroup = 160;
+constexpr int kNhwcBigGroupFwd = 128;  // 128 * (128 + 72) B = 25.0 KB of kernel parameters
+constexpr int kNhwcBigGroupBwd = 80;   //  80 * (256 + 72) B = 25.6 KB
 
-// 4 channels of one pixel as two packed fp32 pairs
+// the lane's 4 channels of pixel `row` inside a staged box, as two packed fp32 pairs
 template <typename T>
-struct Vec4;
+struct BoxRow;
 template <>
-struct Vec4<float> {
-  struct Raw {
-    f2 a, b;
-  };
-  __device__ static __forceinline__ Raw load(const void* base, size_t elem) {
-    Raw v;  // two 64-bit registers = two f32x2 operands, no repacking
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];"
-                 : "=l"(v.a), "=l"(v.b)
-                 : "l"(static_cast<const float*>(base) + elem));
-    return v;
+struct BoxRow<float> {
+  static constexpr int kPx = kNhwcBoxBytes / (kNhwcSlab * 4);  // 8
+  __device__ static __forceinline__ void load(uint32_t box_lane, int row, f2& a, f2& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(box_lane + row * (kNhwcSlab * 4)));
   }
-  __device__ static __forceinline__ void unpack(const Raw& r, f2& a, f2& b) {
-    a = r.a;
-    b = r.b;
-  }
+  static constexpr int kLaneBytes = 16;
 };
 template <>
-struct Vec4<__nv_bfloat16> {
-  using Raw = uint2;
-  __device__ static __forceinline__ Raw load(const void* base, size_t elem) {
-    Raw v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
-                 : "=r"(v.x), "=r"(v.y)
-                 : "l"(static_cast<const __nv_bfloat16*>(base) + elem));
-    return v;
+struct BoxRow<__nv_bfloat16> {
+  static constexpr int kPx = kNhwcBoxBytes / (kNhwcSlab * 2);  // 16
+  __device__ static __forceinline__ void load(uint32_t box_lane, int row, f2& a, f2& b) {
+    unsigned lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(box_lane + row * (kNhwcSlab * 2)));
+    a = Elem<__nv_bfloat16>::widen(lo);
+    b = Elem<__nv_bfloat16>::widen(hi);
   }
-  __device__ static __forceinline__ void unpack(const Raw& r, f2& a, f2& b) {
-    a = Elem<__nv_bfloat16>::widen(r.x);
-    b = Elem<__nv_bfloat16>::widen(r.y);
-  }
+  static constexpr int kLaneBytes = 8;
 };
 
-template <typename T, bool BWD>
-struct NhwcGroupPx {  // pixels per group: all loads of a group are in flight together (4 KB per warp)
-  static constexpr int value = (sizeof(T) == 4 ? 8 : 16) / (BWD ? 2 : 1);
+template <bool BWD>
+struct NhwcStages {
+  static constexpr int value = BWD ? 2 : 4;  // x (and dy) boxes: 16 KB of staging per warp either way
 };
 
 template <typename T, bool BWD, int MAXL>
-__global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL> P) {
-  constexpr int G = NhwcGroupPx<T, BWD>::value;
+__global__ void __launch_bounds__(kNhwcWarps * 32, 1)
+    class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P) {
+  constexpr int G = BoxRow<T>::kPx;
   constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
-  using V = Vec4<T>;
-  using Raw = typename V::Raw;
-  extern __shared__ __align__(16) float slots[];  // [warp][slot][2][128]
+  constexpr int kTens = BWD ? 2 : 1;
+  constexpr int kStages = NhwcStages<BWD>::value;
+  constexpr int kStageBytes = kTens * kNhwcBoxBytes;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // [warp][stage][x | dy] boxes | [warp][slot][2][128] fp32 | [warp][stage] mbarriers
+  float* slots = reinterpret_cast<float*>(smem + kNhwcWarps * kStages * kStageBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(slots + kNhwcWarps * kNhwcSlots * 256);
 
   const unsigned K = static_cast<unsigned>(P.K);
   const int n_tiles = P.tile_prefix[P.n_layers];
@@ -504,17 +500,21 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
   const int t_last = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_tiles / gridDim.x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* const mine = reinterpret_cast<float4*>(slots + static_cast<size_t>(warp) * kNhwcSlots * 256) + lane;
+  const uint32_t my_bufs = smem_u32(smem + static_cast<size_t>(warp) * kStages * kStageBytes);
+  const uint32_t my_bars = smem_u32(&bars[warp * kStages]);
+  const uint32_t lane_off = static_cast<uint32_t>(lane * BoxRow<T>::kLaneBytes);
   const unsigned dropped = K * 0x01010101u;
   const bool direct = K <= static_cast<unsigned>(kNhwcSlots);  // slot == class, no tags
+  const uint64_t policy = policy_evict_first();
 
-  struct Group {  // one pixel group in registers: every index below is a compile-time constant after unrolling
-    Raw x[G];
-    Raw d[BWD ? G : 1];
-    unsigned k[Q];  // packed keys; K = dropped
-  };
+  if (lane < kStages) mbar_init(my_bars + lane * 8, 1);
+  for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  mbar_fence_init();
+  __syncwarp();
+  unsigned parity_bits = 0;  // bit s = parity of the next completion of stage s
 
   int layer = 0, cur_layer = -1, cur_sg = -1;
-  int phases = kNhwcWarps, phase = 0, c0 = 0;
+  int phases = kNhwcWarps, phase = 0, c0 = 0, col0 = 0;
   bool lane_on = false, affine = false;
   double* out1 = nullptr;  // &S1[c0], &S2[c0] of the current layer
   double* out2 = nullptr;
@@ -568,12 +568,12 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
     r1a = r1b = r2a = r2b = 0;
     run_key = next_key;
   };
-  auto add_px = [&](const Raw& xr, const Raw& dr) {  // unconditional: a dropped run is discarded when it closes
+  auto add_px = [&](uint32_t box_lane, int row) {  // unconditional: a dropped run is discarded when it closes
     f2 a, b;
-    V::unpack(xr, a, b);
+    BoxRow<T>::load(box_lane, row, a, b);
     if (BWD) {
       f2 da, db;
-      V::unpack(dr, da, db);
+      BoxRow<T>::load(box_lane + kNhwcBoxBytes, row, da, db);
       a = mul2(da, fma2(a, sc01, sf01));
       b = mul2(db, fma2(b, sc23, sf23));
     } else if (affine) {
@@ -599,22 +599,10 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
     }
   };
 
-  for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
-  Group A, B;
-#pragma unroll
-  for (int i = 0; i < G; ++i) {  // lanes beyond C never load: keep their registers defined
-    A.x[i] = Raw{};
-    B.x[i] = Raw{};
-    if (BWD) {
-      A.d[i] = Raw{};
-      B.d[i] = Raw{};
-    }
-  }
-
   for (int tile = t_first; tile < t_last; ++tile) {
     while (tile >= P.tile_prefix[layer + 1]) ++layer;
     const NhwcLayer& L = P.L[layer];
+    const CUtensorMap* maps = &P.maps[layer * kTens];
     const int t = tile - P.tile_prefix[layer];
     const int sg = t / L.n_chunks;
     const int chunk = t - sg * L.n_chunks;
@@ -625,8 +613,9 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
       const int spc = L.spc;
       phases = kNhwcWarps / spc;
       phase = warp / spc;
-      c0 = (sg * spc + warp % spc) * kNhwcSlab + lane * 4;
-      lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside
+      col0 = (sg * spc + warp % spc) * kNhwcSlab;
+      c0 = col0 + lane * 4;
+      lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside (TMA zero-fills outside)
       ld = static_cast<size_t>(L.ld);
       out1 = L.S1 + c0;
       out2 = L.S2 + c0;
@@ -651,66 +640,74 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1) class_stats_nhwc_kernel(co
     const int p_begin = chunk * L.px_per_chunk;
     const int p_end = min(p_begin + L.px_per_chunk, L.n_px);
     const int n_groups = (p_end - p_begin + G - 1) / G;
-    const size_t C = static_cast<size_t>(L.C);
+    const int n_my = col0 < L.C ? (n_groups - phase + phases - 1) / phases : 0;  // a warp whose slab is empty idles
 
-    auto load_group = [&](int g, Group& D) {
-      const int p = p_begin + g * G;
-      if (p + G <= p_end) {
+    int issue_it = 0, issue_stage = 0;
+    auto issue = [&]() {  // one elected lane arms the barrier and launches the tile copies of the warp's next group
+      if (issue_it < n_my) {
+        if (lane == 0) {
+          const uint32_t bar = my_bars + issue_stage * 8;
+          const uint32_t dst = my_bufs + issue_stage * kStageBytes;
+          const int p = p_begin + (phase + issue_it * phases) * G;
+          mbar_expect_tx(bar, kStageBytes);
+          tma_load_2d(dst, maps, col0, p, bar, policy);  // rows past n_px / columns past C arrive as zeros
+          if (BWD) tma_load_2d(dst + kNhwcBoxBytes, maps + 1, col0, p, bar, policy);
+        }
+      }
+      ++issue_it;
+      if (++issue_stage == kStages) issue_stage = 0;
+    };
+    unsigned kw[Q], kw_next[Q];
+    auto load_keys = [&](int it, unsigned* dst) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) D.k[q] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + p) + q) : 0u;
-        if (lane_on) {
+      for (int q = 0; q < Q; ++q) dst[q] = dropped;
+      if (it < n_my) {
+        const int p = p_begin + (phase + it * phases) * G;
+        if (p + G <= p_end) {
+#pragma unroll
+          for (int q = 0; q < Q; ++q) dst[q] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + p) + q) : 0u;
+        } else {  // ragged tail of the chunk: missing pixels are "dropped"
 #pragma unroll
           for (int i = 0; i < G; ++i) {
-            D.x[i] = V::load(L.x, (p + i) * C + c0);
-            if (BWD) D.d[i] = V::load(L.dy, (p + i) * C + c0);
-          }
-        }
-      } else {  // ragged tail of the chunk: pixel by pixel, missing pixels are "dropped"
-#pragma unroll
-        for (int q = 0; q < Q; ++q) D.k[q] = dropped;
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-          if (p + i < p_end) {
-            const unsigned k = L.keys ? L.keys[p + i] : 0u;
-            const int sh = 8 * (i & 3);
-            D.k[i >> 2] = (D.k[i >> 2] & ~(0xffu << sh)) | (k << sh);
-            if (lane_on) {
-              D.x[i] = V::load(L.x, (p + i) * C + c0);
-              if (BWD) D.d[i] = V::load(L.dy, (p + i) * C + c0);
+            if (p + i < p_end) {
+              const unsigned k = L.keys ? L.keys[p + i] : 0u;
+              const int sh = 8 * (i & 3);
+              dst[i >> 2] = (dst[i >> 2] & ~(0xffu << sh)) | (k << sh);
             }
           }
         }
       }
     };
-    auto consume = [&](const Group& D) {
+
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) issue();
+    load_keys(0, kw);
+    int stage = 0;
+    for (int it = 0; it < n_my; ++it) {
+      load_keys(it + 1, kw_next);  // global load overlaps the wait below
+      mbar_wait(my_bars + stage * 8, (parity_bits >> stage) & 1u);
+      parity_bits ^= 1u << stage;
+      const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const unsigned w = D.k[q];
+        const unsigned w = kw[q];
         if (w == run_key * 0x01010101u) {  // the quad continues the open run: branch-free
 #pragma unroll
-          for (int e = 0; e < 4; ++e) add_px(D.x[4 * q + e], D.d[BWD ? 4 * q + e : 0]);
+          for (int e = 0; e < 4; ++e) add_px(box_lane, 4 * q + e);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const unsigned k = (w >> (8 * e)) & 0xffu;
             if (k != run_key) close_run(k);
-            add_px(D.x[4 * q + e], D.d[BWD ? 4 * q + e : 0]);
+            add_px(box_lane, 4 * q + e);
           }
         }
       }
-    };
-
-    // groups of this warp: phase, phase + phases, ...; the next group's loads are in flight while one is consumed
-    int g = phase;
-    if (g < n_groups) load_group(g, A);
-    while (g < n_groups) {
-      if (g + phases < n_groups) load_group(g + phases, B);
-      consume(A);
-      g += phases;
-      if (g >= n_groups) break;
-      if (g + phases < n_groups) load_group(g + phases, A);
-      consume(B);
-      g += phases;
+      __syncwarp();
+      issue();  // refill the stage just consumed
+#pragma unroll
+      for (int q = 0; q < Q; ++q) kw[q] = kw_next[q];
+      if (++stage == kStages) stage = 0;
     }
     close_run(K);  // bounds the length of an fp32 run to one chunk
   }
@@ -813,6 +810,23 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// NHWC: [rows = N*HW][cols = C], box = [G px][128 channels], no swizzle (a pixel row is read with one LDS per lane)
+int make_map_nhwc(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  DCFP_REQUIRE(enc != nullptr, DCFP_EUNSUPPORTED, "class_stats: cuTensorMapEncodeTiled is not available in this driver");
+  const size_t es = dtype == DCFP_F32 ? 4 : 2;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * es};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kNhwcSlab), static_cast<cuuint32_t>(kNhwcBoxBytes / (kNhwcSlab * es))};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(map, dtype == DCFP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCFP_REQUIRE(r == CUDA_SUCCESS, DCFP_EINVAL, "class_stats: cuTensorMapEncodeTiled (NHWC) failed (CUresult %d) rows=%lld cols=%lld",
+               static_cast<int>(r), rows, cols);
+  return 0;
+}
+
 // [rows = N*C][cols = HW] view of an NCHW tensor, box = [32 rows][128 B], SWIZZLE_128B
 int make_map(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols) {
   EncodeTiledFn enc = encode_tiled_fn();
@@ -869,14 +883,13 @@ bool tiled_ok(const dcfp_layer_desc& d) {
   return true;
 }
 
-// the NHWC fast path: whole 4-channel vectors, 16-B aligned rows, per-warp tables that fit in shared memory
+// the NHWC fast path (TMA): 16-B aligned base and row pitch, whole 4-channel vectors
 bool nhwc_ok(const dcfp_layer_desc& d) {
   if (d.layout != DCFP_NHWC) return false;
   const size_t es = d.dtype == DCFP_F32 ? 4 : 2;
-  if (d.C % 4 != 0 || (static_cast<size_t>(d.C) * es) % (4 * es) != 0) return false;
-  const uintptr_t al = 4 * es;  // one lane's vector
-  if (reinterpret_cast<uintptr_t>(d.x) % al != 0) return false;
-  if (d.dy && reinterpret_cast<uintptr_t>(d.dy) % al != 0) return false;
+  if (d.C % 4 != 0 || (static_cast<size_t>(d.C) * es) % 16 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(d.x) % 16 != 0) return false;
+  if (d.dy && reinterpret_cast<uintptr_t>(d.dy) % 16 != 0) return false;
   if (d.keys && reinterpret_cast<uintptr_t>(d.keys) % 4 != 0) return false;
   if (static_cast<long long>(d.N) * d.h * d.w < 64) return false;  // tiny pooled maps: generic
   return true;
@@ -884,16 +897,16 @@ bool nhwc_ok(const dcfp_layer_desc& d) {
 
 template <typename T, bool BWD, int MAXL>
 int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long target_bytes, cudaStream_t stream) {
+  constexpr int kTens = BWD ? 2 : 1;
+  constexpr int G = BoxRow<T>::kPx;
   const int K = descs[which[0]].K;
-  NhwcParams<MAXL> P;
+  NhwcParams<MAXL, kTens> P;
   P.n_layers = n;
   P.K = K;
   P.tile_prefix[0] = 0;
   for (int i = 0; i < n; ++i) {
     const dcfp_layer_desc& d = descs[which[i]];
     NhwcLayer& L = P.L[i];
-    L.x = d.x;
-    L.dy = d.dy;
     L.keys = d.keys;
     L.scale = d.scale;
     L.shift = d.shift;
@@ -908,7 +921,7 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
     L.spc = spc;
     L.n_slab_groups = (n_slabs + spc - 1) / spc;
-    const int gran = NhwcGroupPx<T, BWD>::value * (kNhwcWarps / spc);  // every phase gets whole pixel groups
+    const int gran = G * (kNhwcWarps / spc);  // every phase gets whole pixel groups
     const long long row_bytes = static_cast<long long>(std::min(d.C, spc * kNhwcSlab)) * sizeof(T);
     long long px = std::max<long long>(target_bytes / row_bytes, gran);
     px = (px + gran - 1) / gran * gran;
@@ -917,10 +930,15 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     const long long tiles = static_cast<long long>(L.n_chunks) * L.n_slab_groups;
     DCFP_REQUIRE(P.tile_prefix[i] + tiles < (1LL << 31), DCFP_ETOOBIG, "class_stats: too many tiles");
     P.tile_prefix[i + 1] = P.tile_prefix[i] + static_cast<int>(tiles);
+    int rc = make_map_nhwc(&P.maps[i * kTens], d.x, d.dtype, L.n_px, d.C);
+    if (rc == 0 && BWD) rc = make_map_nhwc(&P.maps[i * kTens + 1], d.dy, d.dtype, L.n_px, d.C);
+    if (rc) return rc;
   }
   const int n_tiles = P.tile_prefix[n];
   if (n_tiles == 0) return 0;
-  const size_t smem = static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float);
+  const size_t smem = static_cast<size_t>(kNhwcWarps) * NhwcStages<BWD>::value * kTens * kNhwcBoxBytes +
+                      static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float) + 8 * kNhwcWarps * NhwcStages<BWD>::value +
+                      1024 /* base alignment slack */;
   auto kern = class_stats_nhwc_kernel<T, BWD, MAXL>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
@@ -1036,8 +1054,9 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
   if (n_nhwc > 0) {
     // persistent CTAs (one per SM) each walk ~8 tiles: ~1/8 of an SM's share of the call per tile, 128 KB .. 2 MB
     long long target = std::min<long long>(2 << 20, std::max<long long>(128 << 10, nhwc_bytes / (8LL * kNumSMs)));
+    const int nhwc_big = bwd ? kNhwcBigGroupBwd : kNhwcBigGroupFwd;
     for (int first = 0; first < n_nhwc;) {
-      const int m = std::min(n_nhwc - first, kNhwcBigGroup);
+      const int m = std::min(n_nhwc - first, nhwc_big);
       int rc;
       if (m <= kSmallGroup) {
         if (dtype == DCFP_F32)
@@ -1047,11 +1066,11 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
           rc = bwd ? run_nhwc<__nv_bfloat16, true, kSmallGroup>(descs, nhwc + first, m, target, stream)
                    : run_nhwc<__nv_bfloat16, false, kSmallGroup>(descs, nhwc + first, m, target, stream);
       } else if (dtype == DCFP_F32) {
-        rc = bwd ? run_nhwc<float, true, kNhwcBigGroup>(descs, nhwc + first, m, target, stream)
-                 : run_nhwc<float, false, kNhwcBigGroup>(descs, nhwc + first, m, target, stream);
+        rc = bwd ? run_nhwc<float, true, kNhwcBigGroupBwd>(descs, nhwc + first, m, target, stream)
+                 : run_nhwc<float, false, kNhwcBigGroupFwd>(descs, nhwc + first, m, target, stream);
       } else {
-        rc = bwd ? run_nhwc<__nv_bfloat16, true, kNhwcBigGroup>(descs, nhwc + first, m, target, stream)
-                 : run_nhwc<__nv_bfloat16, false, kNhwcBigGroup>(descs, nhwc + first, m, target, stream);
+        rc = bwd ? run_nhwc<__nv_bfloat16, true, kNhwcBigGroupBwd>(descs, nhwc + first, m, target, stream)
+                 : run_nhwc<__nv_bfloat16, false, kNhwcBigGroupFwd>(descs, nhwc + first, m, target, stream);
       }
       if (rc) return rc;
       first += m;
