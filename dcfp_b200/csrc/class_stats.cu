@@ -448,6 +448,7 @@ struct NhwcParams {
   int32_t tile_prefix[MAXL + 1];
   int32_t n_layers;
   int32_t K;
+  int32_t stages;  // boxes in flight per warp
 };
 constexpr int kNhwcBigGroupFwd = 128;  // 128 * (128 + 72) B = 25.0 KB of kernel parameters
 constexpr int kNhwcBigGroupBwd = 80;   //  80 * (256 + 72) B = 25.6 KB
@@ -475,19 +476,16 @@ struct BoxRow<__nv_bfloat16> {
   static constexpr int kLaneBytes = 8;
 };
 
-template <bool BWD>
-struct NhwcStages {
-  static constexpr int value = BWD ? 2 : 4;  // x (and dy) boxes: 16 KB of staging per warp either way
-};
+constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-boxes, or 2 (x, dy) pairs
 
-template <typename T, bool BWD, int MAXL>
+template <typename T, bool BWD, bool AFFINE, int MAXL>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P) {
   constexpr int G = BoxRow<T>::kPx;
   constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int kStages = NhwcStages<BWD>::value;
   constexpr int kStageBytes = kTens * kNhwcBoxBytes;
+  const int kStages = P.stages;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // [warp][stage][x | dy] boxes | [warp][slot][2][128] fp32 | [warp][stage] mbarriers
@@ -515,7 +513,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
 
   int layer = 0, cur_layer = -1, cur_sg = -1;
   int phases = kNhwcWarps, phase = 0, c0 = 0, col0 = 0;
-  bool lane_on = false, affine = false;
+  bool lane_on = false;
   double* out1 = nullptr;  // &S1[c0], &S2[c0] of the current layer
   double* out2 = nullptr;
   size_t ld = 0;
@@ -576,7 +574,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       BoxRow<T>::load(box_lane + kNhwcBoxBytes, row, da, db);
       a = mul2(da, fma2(a, sc01, sf01));
       b = mul2(db, fma2(b, sc23, sf23));
-    } else if (affine) {
+    } else if (AFFINE) {
       a = fma2(a, sc01, sf01);
       b = fma2(b, sc23, sf23);
     }
@@ -619,10 +617,9 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       ld = static_cast<size_t>(L.ld);
       out1 = L.S1 + c0;
       out2 = L.S2 + c0;
-      affine = BWD || L.scale || L.shift;
       sc01 = sc23 = pack2(1.f, 1.f);
       sf01 = sf23 = 0;
-      if (lane_on && affine) {
+      if (lane_on && (BWD || AFFINE)) {
         float sc[4], sf[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -679,7 +676,6 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       }
     };
 
-#pragma unroll
     for (int s = 0; s < kStages; ++s) issue();
     load_keys(0, kw);
     int stage = 0;
@@ -689,17 +685,24 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       parity_bits ^= 1u << stage;
       const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const unsigned w = kw[q];
-        if (w == run_key * 0x01010101u) {  // the quad continues the open run: branch-free
+      for (int hf = 0; hf < G / 8; ++hf) {  // 8 pixels = one 64-bit key word at a time
+        const unsigned long long kk = static_cast<unsigned long long>(kw[2 * hf]) | (static_cast<unsigned long long>(kw[2 * hf + 1]) << 32);
+        if (kk == run_key * 0x0101010101010101ull) {  // all 8 pixels continue the open run: straight-line accumulate
 #pragma unroll
-          for (int e = 0; e < 4; ++e) add_px(box_lane, 4 * q + e);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const unsigned k = (w >> (8 * e)) & 0xffu;
+          for (int e = 0; e < 8; ++e) add_px(box_lane, 8 * hf + e);
+        } else {  // a class boundary inside: walk the runs (warp-uniform scalar work; pixel rows are indexed in smem)
+          int i = 0;
+#pragma unroll 1
+          while (i < 8) {
+            const unsigned long long rest = kk >> (8 * i);
+            const unsigned k = static_cast<unsigned>(rest) & 0xffu;
             if (k != run_key) close_run(k);
-            add_px(box_lane, 4 * q + e);
+            const unsigned long long diff = rest ^ (k * 0x0101010101010101ull);  // zero bytes = pixels of this run
+            int n = diff ? (__ffsll(static_cast<long long>(diff)) - 1) >> 3 : 8;
+            n = min(n, 8 - i);
+#pragma unroll 1
+            for (int e = 0; e < n; ++e) add_px(box_lane, 8 * hf + i + e);
+            i += n;
           }
         }
       }
@@ -904,9 +907,11 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
   P.n_layers = n;
   P.K = K;
   P.tile_prefix[0] = 0;
+  bool affine = false;
   for (int i = 0; i < n; ++i) {
     const dcfp_layer_desc& d = descs[which[i]];
     NhwcLayer& L = P.L[i];
+    affine = affine || d.scale || d.shift;
     L.keys = d.keys;
     L.scale = d.scale;
     L.shift = d.shift;
@@ -936,10 +941,17 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
   }
   const int n_tiles = P.tile_prefix[n];
   if (n_tiles == 0) return 0;
-  const size_t smem = static_cast<size_t>(kNhwcWarps) * NhwcStages<BWD>::value * kTens * kNhwcBoxBytes +
-                      static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float) + 8 * kNhwcWarps * NhwcStages<BWD>::value +
+  static const int forced = []() {
+    const char* e = getenv("DCFP_K1_NHWC_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  P.stages = kNhwcStageBudget / (kTens * kNhwcBoxBytes);
+  if (forced >= 1 && forced * kTens * kNhwcBoxBytes <= (20 << 10)) P.stages = forced;
+  const size_t smem = static_cast<size_t>(kNhwcWarps) * P.stages * kTens * kNhwcBoxBytes +
+                      static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float) + 8 * kNhwcWarps * P.stages +
                       1024 /* base alignment slack */;
-  auto kern = class_stats_nhwc_kernel<T, BWD, MAXL>;
+  void (*kern)(NhwcParams<MAXL, kTens>) = class_stats_nhwc_kernel<T, BWD, true, MAXL>;
+  if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
   kern<<<std::min(n_tiles, kNumSMs), kNhwcWarps * 32, smem, stream>>>(P);  // persistent: one CTA per SM
