@@ -654,8 +654,11 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       ++issue_it;
       if (++issue_stage == kStages) issue_stage = 0;
     };
-    unsigned kw[Q], kw_next[Q];
-    auto load_keys = [&](int it, unsigned* dst) {
+    // Class keys: lane j holds the packed keys of the warp's iteration (block + j), fetched 32 iterations at a time
+    // and one block ahead, then broadcast with a shuffle.  (A per-iteration global load -- even issued one iteration
+    // early -- put its full latency on every iteration's critical path: 8 warps/SM cannot hide ~1 us per 4 KB box.)
+    auto fetch_keys = [&](int it0, unsigned* dst) {
+      const int it = it0 + lane;
 #pragma unroll
       for (int q = 0; q < Q; ++q) dst[q] = dropped;
       if (it < n_my) {
@@ -675,12 +678,21 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
         }
       }
     };
+    unsigned kcur[Q], knxt[Q], kw[Q];
+    fetch_keys(0, kcur);
+    fetch_keys(32, knxt);
 
     for (int s = 0; s < kStages; ++s) issue();
-    load_keys(0, kw);
     int stage = 0;
     for (int it = 0; it < n_my; ++it) {
-      load_keys(it + 1, kw_next);  // global load overlaps the wait below
+      const int j = it & 31;
+      if (j == 0 && it > 0) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) kcur[q] = knxt[q];
+        fetch_keys(it + 32, knxt);
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q) kw[q] = __shfl_sync(0xffffffffu, kcur[q], j);
       mbar_wait(my_bars + stage * 8, (parity_bits >> stage) & 1u);
       parity_bits ^= 1u << stage;
       const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
@@ -708,8 +720,6 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       }
       __syncwarp();
       issue();  // refill the stage just consumed
-#pragma unroll
-      for (int q = 0; q < Q; ++q) kw[q] = kw_next[q];
       if (++stage == kStages) stage = 0;
     }
     close_run(K);  // bounds the length of an fp32 run to one chunk
