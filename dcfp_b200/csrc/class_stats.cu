@@ -518,12 +518,12 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   double* out2 = nullptr;
   size_t ld = 0;
   f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
-  // open run: class (K = none / dropped) and the partial sums of this lane's 4 channels
-  unsigned run_key = K;
-  f2 r1a = 0, r1b = 0, r2a = 0, r2b = 0;
-  // slot cache: class held by each row (0xff = free), round-robin victim
+  // slot cache: class held by each row (0xff = free), round-robin victim, last hit
   unsigned long long tags = ~0ull;
   int victim = 0;
+  unsigned last_key = 0xffffffffu;
+  int last_slot = 0;
+  const uint32_t mine_u32 = smem_u32(mine);
 
   auto row_to_arena = [&](int slot, unsigned cls) {  // fp32 row -> fp64 arena, row zeroed
     const float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
@@ -544,30 +544,39 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   };
   auto slot_of = [&](unsigned cls) -> int {  // warp-uniform
     if (direct) return static_cast<int>(cls);
+    if (cls == last_key) return last_slot;
     const unsigned long long x = tags ^ (0x0101010101010101ull * cls);
     const unsigned long long z = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;  // lowest hit is exact
-    if (z) return (__ffsll(static_cast<long long>(z)) - 1) >> 3;
-    const int slot = victim;
-    victim = (victim + 1) & (kNhwcSlots - 1);
-    const unsigned old = static_cast<unsigned>(tags >> (8 * slot)) & 0xffu;
-    if (old != 0xffu) row_to_arena(slot, old);
-    tags = (tags & ~(0xffull << (8 * slot))) | (static_cast<unsigned long long>(cls) << (8 * slot));
+    int slot;
+    if (z) {
+      slot = (__ffsll(static_cast<long long>(z)) - 1) >> 3;
+    } else {
+      slot = victim;
+      victim = (victim + 1) & (kNhwcSlots - 1);
+      const unsigned old = static_cast<unsigned>(tags >> (8 * slot)) & 0xffu;
+      if (old != 0xffu) row_to_arena(slot, old);
+      tags = (tags & ~(0xffull << (8 * slot))) | (static_cast<unsigned long long>(cls) << (8 * slot));
+    }
+    last_key = cls;
+    last_slot = slot;
     return slot;
   };
-  auto close_run = [&](unsigned next_key) {
-    if (run_key < K) {
-      const int slot = slot_of(run_key);
-      float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
-      a.x += lo2(r1a); a.y += hi2(r1a); a.z += lo2(r1b); a.w += hi2(r1b);
-      b.x += lo2(r2a); b.y += hi2(r2a); b.z += lo2(r2b); b.w += hi2(r2b);
-      mine[slot * 64] = a;
-      mine[slot * 64 + 32] = b;
-    }
-    r1a = r1b = r2a = r2b = 0;
-    run_key = next_key;
+  // row[class] += (sum, sum of squares) of this lane's 4 channels over a few pixels of one class.  No run state is
+  // carried between pixel groups: every path below is straight-line code over values that die at the row update.
+  auto row_add = [&](unsigned key, f2 s1a, f2 s1b, f2 s2a, f2 s2b) {
+    if (key >= K) return;  // dropped pixels (warp-uniform)
+    const uint32_t addr = mine_u32 + static_cast<uint32_t>(slot_of(key)) * 1024u;
+    f2 a, b, c, d;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(c), "=l"(d) : "r"(addr + 512u));
+    a = add2(a, s1a);
+    b = add2(b, s1b);
+    c = add2(c, s2a);
+    d = add2(d, s2b);
+    asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+    asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(addr + 512u), "l"(c), "l"(d) : "memory");
   };
-  auto add_px = [&](uint32_t box_lane, int row) {  // unconditional: a dropped run is discarded when it closes
-    f2 a, b;
+  auto load_px = [&](uint32_t box_lane, int row, f2& a, f2& b) {  // value functor of one pixel row
     BoxRow<T>::load(box_lane, row, a, b);
     if (BWD) {
       f2 da, db;
@@ -578,13 +587,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       a = fma2(a, sc01, sf01);
       b = fma2(b, sc23, sf23);
     }
-    r1a = add2(r1a, a);
-    r1b = add2(r1b, b);
-    r2a = fma2(a, a, r2a);
-    r2b = fma2(b, b, r2b);
   };
   auto fold = [&]() {  // every row of this warp -> arena (end of a (layer, slab group))
-    close_run(K);
     if (direct) {
       for (unsigned k = 0; k < K; ++k) row_to_arena(static_cast<int>(k), k);
     } else {
@@ -594,6 +598,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       }
       tags = ~0ull;
       victim = 0;
+      last_key = 0xffffffffu;
     }
   };
 
@@ -698,23 +703,46 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
 #pragma unroll
       for (int hf = 0; hf < G / 8; ++hf) {  // 8 pixels = one 64-bit key word at a time
-        const unsigned long long kk = static_cast<unsigned long long>(kw[2 * hf]) | (static_cast<unsigned long long>(kw[2 * hf + 1]) << 32);
-        if (kk == run_key * 0x0101010101010101ull) {  // all 8 pixels continue the open run: straight-line accumulate
+        const unsigned w_lo = kw[2 * hf], w_hi = kw[2 * hf + 1];
+        const unsigned k0 = w_lo & 0xffu;
+        if (w_lo == k0 * 0x01010101u && w_hi == w_lo) {  // one class: 8 rows summed in registers, one row update
+          f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) add_px(box_lane, 8 * hf + e);
-        } else {  // a class boundary inside: walk the runs (warp-uniform scalar work; pixel rows are indexed in smem)
-          int i = 0;
+          for (int e = 0; e < 8; ++e) {
+            f2 a, b;
+            load_px(box_lane, 8 * hf + e, a, b);
+            s1a = add2(s1a, a);
+            s1b = add2(s1b, b);
+            s2a = fma2(a, a, s2a);
+            s2b = fma2(b, b, s2b);
+          }
+          row_add(k0, s1a, s1b, s2a, s2b);
+        } else {  // a class boundary inside: per quad, and pixel by pixel only in the quad that straddles it
 #pragma unroll 1
-          while (i < 8) {
-            const unsigned long long rest = kk >> (8 * i);
-            const unsigned k = static_cast<unsigned>(rest) & 0xffu;
-            if (k != run_key) close_run(k);
-            const unsigned long long diff = rest ^ (k * 0x0101010101010101ull);  // zero bytes = pixels of this run
-            int n = diff ? (__ffsll(static_cast<long long>(diff)) - 1) >> 3 : 8;
-            n = min(n, 8 - i);
+          for (int q = 0; q < 2; ++q) {
+            const unsigned w = q ? w_hi : w_lo;
+            const unsigned kq = w & 0xffu;
+            const int row0 = 8 * hf + 4 * q;
+            if (w == kq * 0x01010101u) {
+              f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f2 a, b;
+                load_px(box_lane, row0 + e, a, b);
+                s1a = add2(s1a, a);
+                s1b = add2(s1b, b);
+                s2a = fma2(a, a, s2a);
+                s2b = fma2(b, b, s2b);
+              }
+              row_add(kq, s1a, s1b, s2a, s2b);
+            } else {
 #pragma unroll 1
-            for (int e = 0; e < n; ++e) add_px(box_lane, 8 * hf + i + e);
-            i += n;
+              for (int e = 0; e < 4; ++e) {
+                f2 a, b;
+                load_px(box_lane, row0 + e, a, b);
+                row_add((w >> (8 * e)) & 0xffu, a, b, mul2(a, a), mul2(b, b));
+              }
+            }
           }
         }
       }
@@ -722,7 +750,6 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       issue();  // refill the stage just consumed
       if (++stage == kStages) stage = 0;
     }
-    close_run(K);  // bounds the length of an fp32 run to one chunk
   }
   if (cur_layer >= 0) fold();
 }
