@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
 constexpr int kNhwcWarps = 8;
 constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
 constexpr int kNhwcSlots = 8;        // class rows per warp
-constexpr int kNhwcBoxBytes = 4096;  // [G px][128 ch]: G = 8 (fp32) / 16 (bf16)
+// one staged box = [G px][128 ch]: 8 KB forward (G = 16 fp32 / 32 bf16), 4 KB per tensor backward (x and dy boxes):
+// 8 KB per pipeline stage either way, so the fixed per-iteration work (wait, key broadcast, refill) is paid per 8 KB
+constexpr int nhwc_box_bytes(bool bwd) { return bwd ? 4096 : 8192; }
 
 struct NhwcLayer {
   const uint8_t* keys;  // [N*HW]
@@ -458,7 +460,7 @@ template <typename T>
 struct BoxRow;
 template <>
 struct BoxRow<float> {
-  static constexpr int kPx = kNhwcBoxBytes / (kNhwcSlab * 4);  // 8
+  static constexpr int kRowBytes = kNhwcSlab * 4;
   __device__ static __forceinline__ void load(uint32_t box_lane, int row, f2& a, f2& b) {
     asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(box_lane + row * (kNhwcSlab * 4)));
   }
@@ -466,7 +468,7 @@ struct BoxRow<float> {
 };
 template <>
 struct BoxRow<__nv_bfloat16> {
-  static constexpr int kPx = kNhwcBoxBytes / (kNhwcSlab * 2);  // 16
+  static constexpr int kRowBytes = kNhwcSlab * 2;
   __device__ static __forceinline__ void load(uint32_t box_lane, int row, f2& a, f2& b) {
     unsigned lo, hi;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(box_lane + row * (kNhwcSlab * 2)));
@@ -481,7 +483,8 @@ constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-bo
 template <typename T, bool BWD, bool AFFINE, int MAXL>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P) {
-  constexpr int G = BoxRow<T>::kPx;
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD);
+  constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
   constexpr int kTens = BWD ? 2 : 1;
   constexpr int kStageBytes = kTens * kNhwcBoxBytes;
@@ -851,13 +854,13 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // NHWC: [rows = N*HW][cols = C], box = [G px][128 channels], no swizzle (a pixel row is read with one LDS per lane)
-int make_map_nhwc(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols) {
+int make_map_nhwc(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols, int box_bytes) {
   EncodeTiledFn enc = encode_tiled_fn();
   DCFP_REQUIRE(enc != nullptr, DCFP_EUNSUPPORTED, "class_stats: cuTensorMapEncodeTiled is not available in this driver");
   const size_t es = dtype == DCFP_F32 ? 4 : 2;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * es};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kNhwcSlab), static_cast<cuuint32_t>(kNhwcBoxBytes / (kNhwcSlab * es))};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kNhwcSlab), static_cast<cuuint32_t>(box_bytes / (kNhwcSlab * es))};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = enc(map, dtype == DCFP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                          const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -938,7 +941,8 @@ bool nhwc_ok(const dcfp_layer_desc& d) {
 template <typename T, bool BWD, int MAXL>
 int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long target_bytes, cudaStream_t stream) {
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int G = BoxRow<T>::kPx;
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD);
+  constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   const int K = descs[which[0]].K;
   NhwcParams<MAXL, kTens> P;
   P.n_layers = n;
@@ -972,8 +976,8 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     const long long tiles = static_cast<long long>(L.n_chunks) * L.n_slab_groups;
     DCFP_REQUIRE(P.tile_prefix[i] + tiles < (1LL << 31), DCFP_ETOOBIG, "class_stats: too many tiles");
     P.tile_prefix[i + 1] = P.tile_prefix[i] + static_cast<int>(tiles);
-    int rc = make_map_nhwc(&P.maps[i * kTens], d.x, d.dtype, L.n_px, d.C);
-    if (rc == 0 && BWD) rc = make_map_nhwc(&P.maps[i * kTens + 1], d.dy, d.dtype, L.n_px, d.C);
+    int rc = make_map_nhwc(&P.maps[i * kTens], d.x, d.dtype, L.n_px, d.C, kNhwcBoxBytes);
+    if (rc == 0 && BWD) rc = make_map_nhwc(&P.maps[i * kTens + 1], d.dy, d.dtype, L.n_px, d.C, kNhwcBoxBytes);
     if (rc) return rc;
   }
   const int n_tiles = P.tile_prefix[n];
