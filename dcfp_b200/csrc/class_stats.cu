@@ -428,7 +428,7 @@ constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
 constexpr int kNhwcSlots = 8;        // class rows per warp
 // one staged box = [G px][128 ch]: 8 KB forward (G = 16 fp32 / 32 bf16), 4 KB per tensor backward (x and dy boxes):
 // 8 KB per pipeline stage either way, so the fixed per-iteration work (wait, key broadcast, refill) is paid per 8 KB
-constexpr int nhwc_box_bytes(bool bwd) { return bwd ? 4096 : 8192; }
+__host__ __device__ constexpr int nhwc_box_bytes(bool bwd) { return bwd ? 4096 : 8192; }
 
 struct NhwcLayer {
   const uint8_t* keys;  // [N*HW]
