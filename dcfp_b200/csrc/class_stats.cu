@@ -411,21 +411,28 @@ __global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
 // ---- channels_last (NHWC) path ---------------------------------------------------------------------
 // x[n][p][c] with C contiguous: every pixel has ONE class for all its channels, so with lane = 4 consecutive
 // channels the class key is warp-uniform by construction and a pixel's [128-channel slab] is read straight out of
-// a TMA-staged box with one conflict-free LDS per lane -- no transposition.  Each warp owns a slab and a pixel
-// phase and runs a private multi-stage pipeline of [G pixels x 128 channels] tensor-tile copies (cp.async.bulk.
-// tensor.2d, mbarrier completion, evict-first): the bytes in flight live in shared memory, not in registers or
-// L1 miss queues (a register-staged LDG version of this kernel stalled at 56 % of the roofline with the same
-// nominal bytes in flight).  The OPEN CLASS RUN (sum, sum of squares of the lane's 4 channels) stays in registers;
-// a closed run goes to the warp's private SLOT CACHE: 8 rows of [2][128] fp32 tagged with the class they hold (an
-// 8 x 8-bit tag word in a register; labels are spatially coherent, so a warp meets few classes at a time); a
-// ninth class evicts a row to the fp64 arena.  8 KB per warp for ANY K <= 255: no table sized by K, no shared
-// atomics, no CTA-wide barrier in the main loop.  The kernel is PERSISTENT (one CTA per SM walks a contiguous
-// range of tiles ordered (layer, slab group, chunk)); rows are folded into the arena only when the (layer, slab
-// group) changes.  cuDNN's tensor-core convolutions are NHWC-native: running the feature-map producer in
-// channels_last removes its layout transposes (measured 52 -> 36 ms per c2 step) -- the layout bench.py scores.
+// a TMA-staged box with one conflict-free LDS per lane -- no transposition.
+//  * Each warp owns a slab and a pixel phase and runs a private 2-stage pipeline of [G pixels x 128 channels]
+//    tensor-tile copies (cp.async.bulk.tensor.2d, mbarrier completion, evict-first): the bytes in flight live in
+//    shared memory, not in registers or L1 miss queues (a register-staged LDG version of this kernel stalled at
+//    56 % of the roofline with the same nominal bytes in flight).
+//  * Accumulation is STATE-FREE straight-line code: the 8 pixel rows of one 64-bit key word (or the 4 of a quad, or
+//    a single straddling pixel) are summed in registers and added to the class's row.  Carrying an open run in
+//    registers across pixels made ptxas shuffle the accumulators at every possible run boundary (29 instructions
+//    per pixel row, 23 % of them moves) and left 8 warps/SM issue-latency bound at half the roofline.
+//  * Rows live in the warp's private SLOT CACHE: 12 rows of [2][128] fp32; the class held by row i is a register
+//    of lane i, looked up with one ballot (fully associative).  Labels are spatially coherent, so a warp meets few
+//    classes at a time; a 13th class evicts a row to the fp64 arena.  12 KB per warp for ANY K <= 255: no table
+//    sized by K, no shared atomics, no CTA-wide barrier anywhere.
+//  * Class keys are fetched 32 iterations at a time (lane j holds iteration block + j) and broadcast by shuffle:
+//    a per-iteration global load put ~1 us on every iteration's critical path.
+//  * The kernel is PERSISTENT (one CTA per SM walks a contiguous range of tiles ordered (layer, slab group,
+//    chunk)); rows are folded into the arena only when the (layer, slab group) changes.
+// cuDNN's tensor-core convolutions are NHWC-native: running the feature-map producer in channels_last removes its
+// layout transposes (measured 52 -> 36 ms per c2 step) -- this is the layout bench.py scores.
 constexpr int kNhwcWarps = 8;
 constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
-constexpr int kNhwcSlots = 8;        // class rows per warp
+constexpr int kNhwcSlots = 12;       // class rows per warp (tag of row i lives in lane i)
 // one staged box = [G px][128 ch]: 8 KB forward (G = 16 fp32 / 32 bf16), 4 KB per tensor backward (x and dy boxes):
 // 8 KB per pipeline stage either way, so the fixed per-iteration work (wait, key broadcast, refill) is paid per 8 KB
 __host__ __device__ constexpr int nhwc_box_bytes(bool bwd) { return bwd ? 4096 : 8192; }
@@ -521,8 +528,9 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   double* out2 = nullptr;
   size_t ld = 0;
   f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
-  // slot cache: class held by each row (0xff = free), round-robin victim, last hit
-  unsigned long long tags = ~0ull;
+  // slot cache: lane i (< kNhwcSlots) holds the class of row i (kFree = none); round-robin victim; last hit
+  constexpr unsigned kFree = 0xffffffffu;
+  unsigned my_tag = kFree;
   int victim = 0;
   unsigned last_key = 0xffffffffu;
   int last_slot = 0;
@@ -548,17 +556,16 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   auto slot_of = [&](unsigned cls) -> int {  // warp-uniform
     if (direct) return static_cast<int>(cls);
     if (cls == last_key) return last_slot;
-    const unsigned long long x = tags ^ (0x0101010101010101ull * cls);
-    const unsigned long long z = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;  // lowest hit is exact
+    const unsigned hit = __ballot_sync(0xffffffffu, my_tag == cls);  // fully associative lookup in one vote
     int slot;
-    if (z) {
-      slot = (__ffsll(static_cast<long long>(z)) - 1) >> 3;
+    if (hit) {
+      slot = __ffs(hit) - 1;
     } else {
       slot = victim;
-      victim = (victim + 1) & (kNhwcSlots - 1);
-      const unsigned old = static_cast<unsigned>(tags >> (8 * slot)) & 0xffu;
-      if (old != 0xffu) row_to_arena(slot, old);
-      tags = (tags & ~(0xffull << (8 * slot))) | (static_cast<unsigned long long>(cls) << (8 * slot));
+      victim = victim + 1 == kNhwcSlots ? 0 : victim + 1;
+      const unsigned old = __shfl_sync(0xffffffffu, my_tag, slot);
+      if (old != kFree) row_to_arena(slot, old);
+      if (lane == slot) my_tag = cls;
     }
     last_key = cls;
     last_slot = slot;
@@ -596,10 +603,10 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       for (unsigned k = 0; k < K; ++k) row_to_arena(static_cast<int>(k), k);
     } else {
       for (int slot = 0; slot < kNhwcSlots; ++slot) {
-        const unsigned cls = static_cast<unsigned>(tags >> (8 * slot)) & 0xffu;
-        if (cls != 0xffu) row_to_arena(slot, cls);
+        const unsigned cls = __shfl_sync(0xffffffffu, my_tag, slot);
+        if (cls != kFree) row_to_arena(slot, cls);
       }
-      tags = ~0ull;
+      my_tag = kFree;
       victim = 0;
       last_key = 0xffffffffu;
     }
