@@ -39,6 +39,7 @@ namespace dcfp {
 namespace {
 
 constexpr int kWarpsPrivate = 4;  // warps per CTA when every warp owns an accumulator table (small K)
+constexpr int kWarpsShared = 8;   // warps per CTA sharing one table through shared atomics (large K)
 constexpr int kBoxRowBytes = 128;                 // SWIZZLE_128B span
 constexpr int kBoxBytes = 32 * kBoxRowBytes;      // one [32 channels x 128 B] box = 4 KB
 constexpr int kGroups = kBoxRowBytes / 16;        // 128-bit groups per row (8)
@@ -129,12 +130,19 @@ struct Elem<__nv_bfloat16> {
 // acc[key][lane] += (a1, a2): the shared accumulator is an interleaved float2 [K][32] table, so one
 // 64-bit load / FADD2 / 64-bit store updates both moments of (class, channel).  Lanes touch
 // consecutive 8-byte slots: conflict-free.
-__device__ __forceinline__ void acc_add_row(uint32_t acc_lane, unsigned row, float a1, float a2) {
-  const uint32_t addr = acc_lane + row * 256u;  // per-warp table: plain read-modify-write
-  f2 cur;
-  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cur) : "r"(addr));
-  cur = add2(cur, pack2(a1, a2));
-  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(cur) : "memory");
+template <bool SHARED_ACC>
+__device__ __forceinline__ void acc_add(uint32_t acc_lane, unsigned key, float a1, float a2) {
+  const uint32_t addr = acc_lane + key * 256u;
+  if (SHARED_ACC) {  // one CTA-wide table (large K): shared-memory atomics
+    float* p = reinterpret_cast<float*>(__cvta_shared_to_generic(addr));
+    atomicAdd(p, a1);
+    atomicAdd(p + 1, a2);
+  } else {  // per-warp table: plain read-modify-write
+    f2 cur;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cur) : "r"(addr));
+    cur = add2(cur, pack2(a1, a2));
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(cur) : "memory");
+  }
 }
 
 // value of one pixel re-read from the staged box (per-pixel path of a quad that straddles a class
@@ -182,10 +190,9 @@ struct BoxCursor {
   }
 };
 
-// SHARED_ACC (historic name; K > 24): the per-warp table is a 32-row SLOT CACHE instead of K rows -- the class held by
-// row i is a register of lane i, looked up with one ballot; a 33rd class evicts a row to the fp64 arena.  (The first
-// large-K variant shared one [K x 32] table per CTA through shared atomics: 2 x ~64 LSU cycles per warp-wide
-// update capped it at 43-57 % of the roofline.)  RUNLEN (unused now) keeps a class run in registers.
+// RUNLEN: keep the current class run (key, sum, sum of squares) in registers and touch the shared table only
+// when the class changes -- the table of the large-K variant is updated with shared atomics (2 x ~64 cycles
+// per warp-wide update), so the number of updates, not of pixels, is what it can afford.
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, bool RUNLEN>
 __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMap* maps, const int K, const int stages,
                                              const int tile, unsigned char* smem) {
@@ -193,7 +200,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   constexpr int kWords = kBoxPx / 4;                                  // packed key words (quads) per box
   constexpr int kQuadsPerGroup = kWords / kGroups;                    // 1 (fp32) / 2 (bf16)
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int kAccCopies = WARPS;
+  constexpr int kAccCopies = SHARED_ACC ? 1 : WARPS;
   constexpr int kPairs = Elem<T>::kPairs;
   constexpr int kStageBytes = kTens * kBoxBytes;
   constexpr int kThreadsT = WARPS * 32;
@@ -204,11 +211,10 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
 
   // ---- shared-memory carve-up: [boxes | accumulators (float2 [copies][K][32]) | mbarriers] -------
   unsigned char* bufs = smem;  // [WARPS][stages][kTens][kBoxBytes], 1024-B aligned
-  const int rows = SHARED_ACC ? 32 : K;  // table rows per warp
   float2* acc = reinterpret_cast<float2*>(smem + static_cast<size_t>(WARPS) * stages * kStageBytes);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(acc + kAccCopies * rows * 32);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(acc + kAccCopies * K * 32);
 
-  for (int i = tid; i < kAccCopies * rows * 32; i += kThreadsT) acc[i] = make_float2(0.f, 0.f);
+  for (int i = tid; i < kAccCopies * K * 32; i += kThreadsT) acc[i] = make_float2(0.f, 0.f);
   if (tid < WARPS * stages) mbar_init(smem_u32(&bars[tid]), 1);
   mbar_fence_init();
   __syncthreads();
@@ -219,48 +225,8 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   const uint64_t policy = policy_evict_first();
   const uint32_t my_bufs = smem_u32(bufs + static_cast<size_t>(warp) * stages * kStageBytes);
   const uint32_t my_bars = smem_u32(&bars[warp * stages]);
-  const uint32_t acc_lane = smem_u32(acc + warp * rows * 32 + lane);
+  const uint32_t acc_lane = smem_u32(acc + (SHARED_ACC ? 0 : warp * K * 32) + lane);
   const int row0 = cg * 32;
-
-  // slot cache (SHARED_ACC): lane i holds the class of row i; round-robin victim; last hit
-  constexpr unsigned kFree = 0xffffffffu;
-  unsigned my_tag = kFree, last_key = kFree;
-  int victim = 0, last_slot = 0;
-  auto row_to_arena = [&](int slot, unsigned cls) {  // this lane's (sum, sum of squares) of `cls` -> arena, row zeroed
-    const uint32_t addr = acc_lane + static_cast<uint32_t>(slot) * 256u;
-    float a1, a2;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a1), "=f"(a2) : "r"(addr));
-    if (lane < n_active && (a1 != 0.f || a2 != 0.f)) {
-      const size_t o = static_cast<size_t>(cls) * L.ld + row0 + lane;
-      atomicAdd(&L.S1[o], static_cast<double>(a1));
-      atomicAdd(&L.S2[o], static_cast<double>(a2));
-    }
-    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(0.f), "f"(0.f) : "memory");
-  };
-  auto acc_add = [&](unsigned key, float a1, float a2) {
-    if (!SHARED_ACC) {
-      acc_add_row(acc_lane, key, a1, a2);
-      return;
-    }
-    int slot;
-    if (key == last_key) {
-      slot = last_slot;
-    } else {
-      const unsigned hit = __ballot_sync(0xffffffffu, my_tag == key);
-      if (hit) {
-        slot = __ffs(hit) - 1;
-      } else {
-        slot = victim;
-        victim = (victim + 1) & 31;
-        const unsigned old = __shfl_sync(0xffffffffu, my_tag, slot);
-        if (old != kFree) row_to_arena(slot, old);
-        if (lane == slot) my_tag = key;
-      }
-      last_key = key;
-      last_slot = slot;
-    }
-    acc_add_row(acc_lane, static_cast<unsigned>(slot), a1, a2);
-  };
 
   BoxCursor issue_at, key_at;
   issue_at.n = (box_begin + warp) / L.boxes_per_plane;
@@ -317,7 +283,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   float run1 = 0.f, run2 = 0.f;
   auto run_add = [&](unsigned key, float a1, float a2) {  // key is warp-uniform: no divergence
     if (key != run_key) {
-      if (run_key < static_cast<unsigned>(K)) acc_add(run_key, run1, run2);
+      if (run_key < static_cast<unsigned>(K)) acc_add<SHARED_ACC>(acc_lane, run_key, run1, run2);
       run_key = key;
       run1 = a1;
       run2 = a2;
@@ -355,7 +321,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
         s1a = add2(s1a, s1b);
         s2a = add2(s2a, s2b);
         if (RUNLEN) run_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
-        else acc_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
+        else acc_add<SHARED_ACC>(acc_lane, key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
       } else if (RUNLEN) {
         run_add(static_cast<unsigned>(K), 0.f, 0.f);  // dropped pixels close the open run
       }
@@ -376,7 +342,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
               const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
               const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
               if (RUNLEN) run_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
-              else acc_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+              else acc_add<SHARED_ACC>(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
             } else if (RUNLEN) {
               run_add(static_cast<unsigned>(K), 0.f, 0.f);
             }
@@ -387,7 +353,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
               if (ke < static_cast<unsigned>(K)) {
                 const float x = load_px<T, BWD, AFFINE>(gaddr + (h * 4 + e) * static_cast<int>(sizeof(T)), sc, sf);
                 if (RUNLEN) run_add(ke, x, x * x);
-                else acc_add(ke, x, x * x);
+                else acc_add<SHARED_ACC>(acc_lane, ke, x, x * x);
               } else if (RUNLEN) {
                 run_add(static_cast<unsigned>(K), 0.f, 0.f);
               }
@@ -405,13 +371,6 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
     }
   }
   if (RUNLEN) run_add(static_cast<unsigned>(K), 0.f, 0.f);  // close the last run
-  if (SHARED_ACC) {  // every warp folds the rows it holds (no CTA-wide combine: rows differ per warp)
-    for (int slot = 0; slot < 32; ++slot) {
-      const unsigned cls = __shfl_sync(0xffffffffu, my_tag, slot);
-      if (cls != kFree) row_to_arena(slot, cls);
-    }
-    return;
-  }
   __syncthreads();
 
   // ---- CTA partials -> fp64 arena (coalesced RED.F64; zero partials are skipped) ----------------
@@ -433,7 +392,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
 }
 
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL, bool RUNLEN>
-__global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 3 : 4)
+__global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
     class_stats_kernel(const __grid_constant__ GroupParams<MAXL, BWD ? 2 : 1> P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned; SWIZZLE_128B boxes need 1024 B
@@ -936,9 +895,9 @@ int make_map(CUtensorMap* map, const void* base, int dtype, long long rows, long
 }
 
 size_t tile_smem_bytes(int K, bool bwd, bool shared_acc, int stages) {
-  const int warps = kWarpsPrivate;
-  const int rows = shared_acc ? 32 : K;  // slot cache vs one row per class
-  return static_cast<size_t>(warps) * stages * (bwd ? 2 : 1) * kBoxBytes + static_cast<size_t>(warps) * rows * 32 * 8 +
+  const int warps = shared_acc ? kWarpsShared : kWarpsPrivate;
+  const int copies = shared_acc ? 1 : warps;
+  return static_cast<size_t>(warps) * stages * (bwd ? 2 : 1) * kBoxBytes + static_cast<size_t>(copies) * K * 32 * 8 +
          8 * warps * stages + 1024 /* base alignment slack */;
 }
 
@@ -1069,10 +1028,10 @@ int pick_stages() {
 
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int MAXL>
 int launch_tiled(GroupParams<MAXL, BWD ? 2 : 1>& P, int n_tiles, cudaStream_t stream) {
-  constexpr int kWarpsT = kWarpsPrivate;
+  constexpr int kWarpsT = SHARED_ACC ? kWarpsShared : kWarpsPrivate;
   P.stages = pick_stages();
   const size_t smem = tile_smem_bytes(P.K, BWD, SHARED_ACC, P.stages);
-  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL, false>;
+  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL, SHARED_ACC>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
   kern<<<n_tiles, kWarpsT * 32, smem, stream>>>(P);
@@ -1115,7 +1074,7 @@ int run_tiled(const dcfp_layer_desc* descs, const int* which, int n, int boxes_p
   }
   const int n_tiles = P.tile_prefix[n];
   if (n_tiles == 0) return 0;
-  if (K > kPrivateAccMaxK) {  // per-warp 32-row slot cache instead of K rows
+  if (K > kPrivateAccMaxK) {  // one CTA-wide accumulator copy, shared atomics; [K x 32 x 2] floats
     if (BWD || affine) return launch_tiled<T, BWD, true, true, MAXL>(P, n_tiles, stream);
     return launch_tiled<T, BWD, false, true, MAXL>(P, n_tiles, stream);
   }
@@ -1179,10 +1138,8 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
   }
   if (n_tiled == 0) return 0;
   // chunk length: ~512 KB per CTA, shortened while the call cannot fill ~4 waves of 4 CTAs/SM
-  // (slot-cache mode, K > 24: every warp folds its own rows, so tiles are 4x longer to amortise the RED.F64 traffic)
-  const bool slot_mode = K > kPrivateAccMaxK;
-  int chunk = slot_mode ? 4 * kTargetBoxesPerChunk : kTargetBoxesPerChunk;
-  while (chunk > 16 && total_boxes / chunk < 4LL * (slot_mode ? 3 : 4) * kNumSMs) chunk >>= 1;
+  int chunk = kTargetBoxesPerChunk;
+  while (chunk > 16 && total_boxes / chunk < 4LL * 4 * kNumSMs) chunk >>= 1;
 
   const int big = bwd ? kBigGroupBwd : kBigGroupFwd;
   for (int first = 0; first < n_tiled;) {
