@@ -443,8 +443,9 @@ struct NhwcLayer {
   const float* shift;
   double* S1;
   double* S2;
-  int32_t C, ld, centered;
-  int32_t n_px;           // N * HW
+  int32_t C, ld, centered;  // C: columns of the [rows][C] view the tensor map describes
+  int32_t n_px;           // rows of that view: N * HW, or N * HW / 2 when fold2
+  int32_t fold2;          // 64-channel layer viewed as [N*HW/2][128]: a row = 2 pixels, lanes 16-31 hold the odd one
   int32_t spc;            // slabs per CTA: 1, 2, 4 or 8
   int32_t n_slab_groups;  // ceil(ceil(C / 128) / spc)
   int32_t px_per_chunk;   // multiple of G * (8 / spc)
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
 
   int layer = 0, cur_layer = -1, cur_sg = -1;
   int phases = kNhwcWarps, phase = 0, c0 = 0, col0 = 0;
-  bool lane_on = false;
+  bool lane_on = false, fold2 = false;
   double* out1 = nullptr;  // &S1[c0], &S2[c0] of the current layer
   double* out2 = nullptr;
   size_t ld = 0;
@@ -629,6 +630,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       col0 = (sg * spc + warp % spc) * kNhwcSlab;
       c0 = col0 + lane * 4;
       lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside (TMA zero-fills outside)
+      fold2 = L.fold2 != 0;
+      if (fold2) c0 &= 63;  // columns 64..127 of a pixel-pair row are channels 0..63 of the odd pixel
       ld = static_cast<size_t>(L.ld);
       out1 = L.S1 + c0;
       out2 = L.S2 + c0;
@@ -672,20 +675,22 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     // Class keys: lane j holds the packed keys of the warp's iteration (block + j), fetched 32 iterations at a time
     // and one block ahead, then broadcast with a shuffle.  (A per-iteration global load -- even issued one iteration
     // early -- put its full latency on every iteration's critical path: 8 warps/SM cannot hide ~1 us per 4 KB box.)
+    const int kf = fold2 ? 2 : 1;  // key bytes per row
     auto fetch_keys = [&](int it0, unsigned* dst) {
       const int it = it0 + lane;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) dst[q] = dropped;
+      for (int q = 0; q < 2 * Q; ++q) dst[q] = dropped;
       if (it < n_my) {
         const int p = p_begin + (phase + it * phases) * G;
         if (p + G <= p_end) {
 #pragma unroll
-          for (int q = 0; q < Q; ++q) dst[q] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + p) + q) : 0u;
+          for (int q = 0; q < 2 * Q; ++q)
+            if (q < Q * kf) dst[q] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(p) * kf) + q) : 0u;
         } else {  // ragged tail of the chunk: missing pixels are "dropped"
 #pragma unroll
-          for (int i = 0; i < G; ++i) {
-            if (p + i < p_end) {
-              const unsigned k = L.keys ? L.keys[p + i] : 0u;
+          for (int i = 0; i < 2 * G; ++i) {
+            if (i < G * kf && p * kf + i < p_end * kf) {
+              const unsigned k = L.keys ? L.keys[static_cast<size_t>(p) * kf + i] : 0u;
               const int sh = 8 * (i & 3);
               dst[i >> 2] = (dst[i >> 2] & ~(0xffu << sh)) | (k << sh);
             }
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
         }
       }
     };
-    unsigned kcur[Q], knxt[Q], kw[Q];
+    unsigned kcur[2 * Q], knxt[2 * Q], kw[2 * Q];
     fetch_keys(0, kcur);
     fetch_keys(32, knxt);
 
@@ -703,14 +708,72 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       const int j = it & 31;
       if (j == 0 && it > 0) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) kcur[q] = knxt[q];
+        for (int q = 0; q < 2 * Q; ++q) kcur[q] = knxt[q];
         fetch_keys(it + 32, knxt);
       }
 #pragma unroll
-      for (int q = 0; q < Q; ++q) kw[q] = __shfl_sync(0xffffffffu, kcur[q], j);
+      for (int q = 0; q < 2 * Q; ++q)
+        if (q < Q * kf) kw[q] = __shfl_sync(0xffffffffu, kcur[q], j);
       mbar_wait(my_bars + stage * 8, (parity_bits >> stage) & 1u);
       parity_bits ^= 1u << stage;
       const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
+      if (fold2) {
+        // pixel-pair rows: row r = pixels 2r (lanes 0-15) and 2r+1 (lanes 16-31); 8 rows = 16 key bytes = 4 words
+        const bool upper = lane >= 16;
+#pragma unroll
+        for (int hf = 0; hf < G / 8; ++hf) {
+          const unsigned w0 = kw[4 * hf], w1 = kw[4 * hf + 1], w2 = kw[4 * hf + 2], w3 = kw[4 * hf + 3];
+          const unsigned k0 = w0 & 0xffu;
+          if (w0 == k0 * 0x01010101u && w1 == w0 && w2 == w0 && w3 == w0) {  // 16 pixels of one class
+            f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f2 a, b;
+              load_px(box_lane, 8 * hf + e, a, b);
+              s1a = add2(s1a, a);
+              s1b = add2(s1b, b);
+              s2a = fma2(a, a, s2a);
+              s2b = fma2(b, b, s2b);
+            }
+            row_add(k0, s1a, s1b, s2a, s2b);
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {  // 4 rows = 8 pixels = 2 key words
+              const unsigned wa = q ? w2 : w0, wb = q ? w3 : w1;
+              const unsigned kq = wa & 0xffu;
+              const int row0 = 8 * hf + 4 * q;
+              if (wa == kq * 0x01010101u && wb == wa) {
+                f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f2 a, b;
+                  load_px(box_lane, row0 + e, a, b);
+                  s1a = add2(s1a, a);
+                  s1b = add2(s1b, b);
+                  s2a = fma2(a, a, s2a);
+                  s2b = fma2(b, b, s2b);
+                }
+                row_add(kq, s1a, s1b, s2a, s2b);
+              } else {
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) {  // one row: its two pixels may belong to two classes
+                  const unsigned pair = ((e < 2 ? wa : wb) >> (16 * (e & 1))) & 0xffffu;
+                  const unsigned ke = pair & 0xffu, ko = pair >> 8;
+                  f2 a, b;
+                  load_px(box_lane, row0 + e, a, b);
+                  if (ke == ko) {
+                    row_add(ke, a, b, mul2(a, a), mul2(b, b));
+                  } else {  // even pixel: lanes 0-15 contribute, odd pixel: lanes 16-31
+                    const f2 ae = upper ? 0 : a, be = upper ? 0 : b, ao = upper ? a : 0, bo = upper ? b : 0;
+                    row_add(ke, ae, be, mul2(ae, ae), mul2(be, be));
+                    row_add(ko, ao, bo, mul2(ao, ao), mul2(bo, bo));
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int hf = 0; hf < G / 8; ++hf) {  // 8 pixels = one 64-bit key word at a time
         const unsigned w_lo = kw[2 * hf], w_hi = kw[2 * hf + 1];
@@ -756,6 +819,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
           }
         }
       }
+      }  // !fold2
       __syncwarp();
       issue();  // refill the stage just consumed
       if (++stage == kStages) stage = 0;
@@ -969,13 +1033,19 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     L.ld = d.ld > 0 ? d.ld : d.C;
     L.centered = d.affine_mode == DCFP_AFFINE_INVSTD_MEAN;
     L.n_px = d.N * d.h * d.w;
-    const int n_slabs = (d.C + kNhwcSlab - 1) / kNhwcSlab;
+    // a 64-channel layer fills only half of a 128-channel slab: view it as [n_px / 2][128] (pixel-pair rows)
+    L.fold2 = (d.C == 64 && L.n_px % 2 == 0) ? 1 : 0;
+    if (L.fold2) {
+      L.C = 128;
+      L.n_px /= 2;
+    }
+    const int n_slabs = (L.C + kNhwcSlab - 1) / kNhwcSlab;
     int spc = 1;
     while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
     L.spc = spc;
     L.n_slab_groups = (n_slabs + spc - 1) / spc;
     const int gran = G * (kNhwcWarps / spc);  // every phase gets whole pixel groups
-    const long long row_bytes = static_cast<long long>(std::min(d.C, spc * kNhwcSlab)) * sizeof(T);
+    const long long row_bytes = static_cast<long long>(std::min(L.C, spc * kNhwcSlab)) * sizeof(T);
     long long px = std::max<long long>(target_bytes / row_bytes, gran);
     px = (px + gran - 1) / gran * gran;
     L.px_per_chunk = static_cast<int>(std::min<long long>(px, (static_cast<long long>(L.n_px) + gran - 1) / gran * gran));
@@ -983,8 +1053,8 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     const long long tiles = static_cast<long long>(L.n_chunks) * L.n_slab_groups;
     DCFP_REQUIRE(P.tile_prefix[i] + tiles < (1LL << 31), DCFP_ETOOBIG, "class_stats: too many tiles");
     P.tile_prefix[i + 1] = P.tile_prefix[i] + static_cast<int>(tiles);
-    int rc = make_map_nhwc(&P.maps[i * kTens], d.x, d.dtype, L.n_px, d.C, kNhwcBoxBytes);
-    if (rc == 0 && BWD) rc = make_map_nhwc(&P.maps[i * kTens + 1], d.dy, d.dtype, L.n_px, d.C, kNhwcBoxBytes);
+    int rc = make_map_nhwc(&P.maps[i * kTens], d.x, d.dtype, L.n_px, L.C, kNhwcBoxBytes);
+    if (rc == 0 && BWD) rc = make_map_nhwc(&P.maps[i * kTens + 1], d.dy, d.dtype, L.n_px, L.C, kNhwcBoxBytes);
     if (rc) return rc;
   }
   const int n_tiles = P.tile_prefix[n];

@@ -280,3 +280,24 @@ def test_channels_last_iid_labels_thrash_the_slot_cache(native, K):
     x = torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(K)).contiguous(memory_format=torch.channels_last)
     label = _labels(N, h, w, K, torch.uint8, seed=K + 1, blob=False)
     _check(ops, x, label, K)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 24, 40, 19, False), (2, 64, 24, 40, 150, False), (3, 64, 5, 7, 19, True),
+                                   (2, 64, 64, 128, 19, True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bwd", [False, True])
+def test_channels_last_64_channel_pixel_pair_rows(native, shape, dtype, bwd):
+    """C == 64: the NHWC kernel views the map as [n_px / 2][128] (a row = 2 pixels, lanes 16-31 hold the odd pixel).
+    i.i.d. labels make almost every row straddle two classes; an odd pixel count falls back to single-pixel rows."""
+    from dcfp_b200 import ops
+    N, C, h, w, K, blob = shape
+    g = torch.Generator().manual_seed(h * 131 + K + bwd)
+    x = (torch.randn(N, C, h, w, generator=g) * 1.5 + 0.3).to(dtype).contiguous(memory_format=torch.channels_last)
+    label = _labels(N, h * (8 if blob else 1), w * (8 if blob else 1), K, torch.uint8, seed=K + h, blob=blob)
+    if bwd:
+        dy = (torch.randn(N, C, h, w, generator=g) * 1e-3).to(dtype).contiguous(memory_format=torch.channels_last)
+        mean = x.float().mean((0, 2, 3))
+        invstd = 1.0 / torch.sqrt(x.float().var((0, 2, 3), unbiased=False) + 1e-5)
+        _check(ops, x, label, K, dy=dy, scale=invstd, shift=-mean * invstd)
+    else:
+        _check(ops, x, label, K)
