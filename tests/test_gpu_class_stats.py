@@ -301,3 +301,35 @@ def test_channels_last_64_channel_pixel_pair_rows(native, shape, dtype, bwd):
         _check(ops, x, label, K, dy=dy, scale=invstd, shift=-mean * invstd)
     else:
         _check(ops, x, label, K)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc", "nhwc64", "generic"])
+@pytest.mark.parametrize("K", [19, 150])
+def test_shared_arena_columns_and_guards(native, layout, K):
+    """Layers write into column slices of ONE [K, sumC] arena (row stride ld): the neighbouring columns, pre-filled
+    with sentinels, must come back untouched (compute-sanitizer is closed on this pool: own guards instead), and a
+    second call accumulates on top of the first."""
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    shape = {"nchw": (2, 96, 32, 64), "nhwc": (2, 160, 24, 40), "nhwc64": (2, 64, 24, 40), "generic": (2, 30, 5, 7)}[layout]
+    N, C, h, w = shape
+    g = torch.Generator().manual_seed(C + K)
+    x = torch.randn(N, C, h, w, generator=g)
+    if layout.startswith("nhwc"):
+        x = x.contiguous(memory_format=torch.channels_last)
+    label = _labels(N, h * 4, w * 4, K, torch.uint8, seed=3 * K)
+    keys = ops.label_keys(label.to(dev), h, w, K)
+    left, right = 37, 11
+    arena = torch.full((2, K, left + C + right), 12345.0, dtype=torch.float64, device=dev)
+    S1 = arena[0][:, left:left + C]
+    S2 = arena[1][:, left:left + C]
+    S1.zero_()
+    S2.zero_()
+    ops.class_stats(x.to(dev), keys, K, S1, S2)
+    ops.class_stats(x.to(dev), keys, K, S1, S2)
+    torch.cuda.synchronize()
+    assert (arena[:, :, :left] == 12345.0).all() and (arena[:, :, left + C:] == 12345.0).all(), "wrote outside its columns"
+    rc, r1, r2 = ref.class_stats(x, label, K)
+    mass = ref.abs_mass(x, label, K)
+    assert ((S1.cpu() - 2 * r1).abs() <= 2 * RTOL * mass + 1e-30).all()
+    assert ((S2.cpu() - 2 * r2).abs() <= 2 * RTOL * r2 + 1e-30).all()
