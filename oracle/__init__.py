@@ -10,11 +10,12 @@ CUDA library is missing.
 
 Pinning status (details in DESIGN.md section "Oracle"):
 
-* ``eic_ref``, ``mask_ref``, ``gather_ref``, ``graph_ref``-style structures: the
-  reference ships no tests / golden vectors, so these restatements are pinned against
-  outputs of the *unmodified reference code executed in the build container*
-  (``oracle/ref_harness.py`` + ``tests/golden/make_golden.py``; fixtures are committed
-  under ``tests/golden/``).
+* ``eic_ref``, ``mask_ref``, ``gather_ref``, ``scoring_ref``: the reference ships no
+  tests / golden vectors, so these restatements are pinned against outputs of the
+  *unmodified reference code executed in the build container* (``oracle/ref_compat.py``
+  + ``tests/golden/make_golden.py``; fixtures are committed under ``tests/golden/``:
+  ``eic_steps.npz``, ``prune_c{1..4}.npz``, ``prune_c1_beta.npz``, ``sweep_c{1,3}.npz``,
+  ``scoring_small.npz``).
 * ``class_stats_ref`` (``bwd`` value functor): pinned through the identity
   ``sum_k S1[k, c] == bn.weight.grad`` of the reference's autograd path.
 * ``class_stats_ref`` (``fwd`` value functor): there is no reference counterpart

@@ -4,7 +4,7 @@ Follows pruners/channel_pruner.py:907-948 (deploy_subnet):
     W = W[out_mask == 1][:, in_mask == 1];  bias / running_mean / running_var = ...[out_mask == 1]
 and :873-905 (resize_subnet_bias):
     act = relu((1 - in_mask) * beta_parent);  offset = W.sum((2, 3)) @ act
-Pinned against the unmodified reference by tests/golden/prune_*.npz (tensor digests).
+Pinned against the unmodified reference by tests/golden/prune_*.npz (SHA-256 of every pruned tensor).
 """
 import numpy as np
 

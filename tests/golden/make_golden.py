@@ -3,7 +3,7 @@
 Run in the build container only (needs /root/reference; oracle/ref_compat.py holds the three
 arithmetic-free shims):
 
-    python tests/golden/make_golden.py [eic] [prune] [scoring]
+    python tests/golden/make_golden.py [eic] [prune] [scoring] [sweep]
 
 The reference ships no tests or golden vectors, so these files ARE the pin of the oracle and of the
 CUDA path on the GPU box, where /root/reference does not exist.
@@ -15,6 +15,7 @@ CUDA path on the GPU box, where /root/reference does not exist.
                        SHA-256 of every tensor of the pruned state_dict
   prune_c1_beta.npz    same with non-zero BN beta -> exercises bias compensation (channel_pruner.py:873-905);
                        stores the compensated running_mean vectors (fp32 GEMV: compared with a tolerance)
+  sweep_c{1,3}.npz     thresholds + raw keep masks for all 25 global_percent values prune.py can visit
   scoring_small.npz    reference Seg_Model + CriterionDSN + dcfp_pruning over 2 steps on 2x3x64x128 inputs:
                        per-step BN-gamma gradients and the final EIC (pins oracle/scoring_ref.py)
 """
@@ -226,6 +227,47 @@ def gen_prune(only_beta=False):
     print("wrote prune_c1_beta.npz; running_mean tensors:", len(moved), "of base", sum(k.endswith("running_mean") for k in base))
 
 
+def gen_sweep():
+    """get_thresh + gen_channel_mask (pruners/dcfp_pruner.py:43-92) for EVERY global_percent prune.py can visit
+    (0.5, 0.52, ... accumulated in floating point exactly as prune.py:91,122 does), eic-like scores with 40 % exact
+    zeros: thresholds (bits) and the raw per-link masks before propagation."""
+    ref = ref_compat.load_reference()
+    tmp = "/tmp/_golden_score.pth"
+    for cfg_name, seed in (("c1", 11), ("c3", 12)):
+        model = build_ref_model(ref, cfg_name)
+        eic = make_scores(model, "eic_like", seed)
+        torch.save({"eic": {k: torch.from_numpy(v) for k, v in eic.items()}}, tmp)
+        out, meta = {}, dict(kind="eic_like", seed=seed, scores_sha256=scores_digest(eic), layer_keep=LAYER_KEEP, percents=[], thresh_bits=[])
+        pruner = None
+        for gi, gp in enumerate(percents()):
+            p = ref.dp.DCFPPruner(global_percent=gp, layer_keep=LAYER_KEEP, score_file=tmp)
+            if pruner is None:  # trace once, reuse the topology for the other percents
+                model_copy = copy.deepcopy(model)
+                p.end_nodes = []  # channel_pruner.py:969-972 (set by prune_model)
+                p.prepare_from_supernet(model_copy)
+                p.except_start_keys = p.except_start_keys + model_copy.ignore_prune_layer + ["conv_deepsup"]
+                p.get_except_layers(model_copy)
+                pruner = p
+            else:
+                for attr in ("name2module", "module2name", "norm_conv_links", "conv_norm_links", "except_layers"):
+                    setattr(p, attr, getattr(pruner, attr))
+            thresh = p.get_thresh()
+            p.gen_channel_mask()
+            bits = []
+            links = []
+            for bn, conv in p.norm_conv_links.items():
+                if conv not in p.except_layers:
+                    bits.append(p.name2module[conv].out_mask.reshape(-1).numpy().astype(np.uint8))
+                    links.append(bn)
+            out["masks_%d" % gi] = np.packbits(np.concatenate(bits))
+            meta["percents"].append(repr(gp))
+            meta["thresh_bits"].append([int(np.float32(float(t)).view(np.uint32)) for t in thresh])
+            meta["links"] = links
+        out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(HERE, "sweep_%s.npz" % cfg_name), **out)
+        print("wrote sweep_%s.npz (%d percents, %d links)" % (cfg_name, len(meta["percents"]), len(meta["links"])))
+
+
 def gen_scoring():
     """Reference model + loss + dcfp_pruning, the restated loop of train.py:255-268, tiny inputs."""
     ref = ref_compat.load_reference()
@@ -257,11 +299,13 @@ def gen_scoring():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["eic", "prune", "scoring"]
+    what = sys.argv[1:] or ["eic", "prune", "scoring", "sweep"]
     assert ref_compat.available(), "reference tree not found"
     if "eic" in what:
         gen_eic()
     if "scoring" in what:
         gen_scoring()
+    if "sweep" in what:
+        gen_sweep()
     if "prune" in what or "beta" in what:
         gen_prune(only_beta="prune" not in what)

@@ -103,3 +103,38 @@ def check_case(z, meta, ci, pruner, sub, cfg, check_topology=True, skip=()):
     bad = [k for k in keys if tensor_digest(sd[k]) != exp[k]]
     assert not bad, "pruned tensors not bit-exact: %s" % bad[:4]
     return sd
+
+
+def load_sweep(name):
+    z = np.load(os.path.join(GOLDEN, "sweep_%s.npz" % name))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+def check_percent_sweep(cfg):
+    """thresholds + raw keep masks of the product (whatever backend ops.* currently is) for all 25 global_percent
+    values prune.py can visit, against the unmodified reference's (tests/golden/sweep_<cfg>.npz): bit-exact."""
+    from dcfp_b200.pruners.channel_pruner import _structural_clone
+    from dcfp_b200.pruners.dcfp_pruner import DCFPPruner
+    z, meta = load_sweep(cfg)
+    model = build_model(cfg)
+    eic = make_scores(model, meta["kind"], meta["seed"])
+    assert scores_digest(eic) == meta["scores_sha256"]
+    with tempfile.NamedTemporaryFile(suffix=".pth") as f:
+        torch.save({"eic": {k: torch.from_numpy(v) for k, v in eic.items()}}, f.name)
+        pruner = DCFPPruner(global_percent=0.5, layer_keep=meta["layer_keep"], score_file=f.name)
+    clone = _structural_clone(model)
+    pruner.prepare_from_supernet(clone)
+    pruner.except_start_keys = pruner.except_start_keys + clone.ignore_prune_layer + ["conv_deepsup"]
+    pruner.get_except_layers(clone)
+    gp, n = 0.5, 0
+    while gp < 1.0:  # prune.py:91,122 -- accumulated in floating point
+        assert repr(gp) == meta["percents"][n]
+        pruner.global_percent = gp
+        thresh, masks = pruner._select()
+        got_t = [int(np.float32(float(t)).view(np.uint32)) for t in thresh]
+        assert got_t == meta["thresh_bits"][n], "thresholds differ at global_percent=%r" % gp
+        bits = np.packbits(np.concatenate([masks[bn].numpy().reshape(-1).astype(np.uint8) for bn in meta["links"]]))
+        assert np.array_equal(bits, z["masks_%d" % n]), "keep masks differ at global_percent=%r" % gp
+        gp += 0.02
+        n += 1
+    assert n == len(meta["percents"]) == 25

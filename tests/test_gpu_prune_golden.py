@@ -60,3 +60,10 @@ def test_pruned_model_runs(native):
     kept = sum(c["out_channels"] for c in ccfg.values())
     raw = sum(c["raw_out_channels"] for c in ccfg.values())
     assert kept < raw
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c3"])
+def test_global_percent_sweep_bit_exact(native, cfg):
+    """K2 (radix-select thresholds, strict-> masks, min-keep fallback) for all 25 global_percent values prune.py can
+    visit, eic-like scores with 40 % exact zeros: thresholds and masks bit-exact vs the unmodified reference."""
+    gu.check_percent_sweep(cfg)

@@ -88,3 +88,10 @@ def test_random_pruner_and_min_keep():
     with torch.no_grad():
         out = sub(torch.randn(1, 3, 64, 64), deepsup=True)
     assert out[0].shape == (1, 19, 64, 64)
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c3"])
+def test_global_percent_sweep_matches_reference_golden(cfg):
+    """oracle backend: pins oracle/mask_ref.py and the host bookkeeping of DCFPPruner._select for every percent."""
+    with oracle_backend():
+        gu.check_percent_sweep(cfg)
