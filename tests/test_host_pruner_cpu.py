@@ -95,3 +95,37 @@ def test_global_percent_sweep_matches_reference_golden(cfg):
     """oracle backend: pins oracle/mask_ref.py and the host bookkeeping of DCFPPruner._select for every percent."""
     with oracle_backend():
         gu.check_percent_sweep(cfg)
+
+
+def test_meta_flops_counter_golden_numbers():
+    """GFLOPs the UNMODIFIED reference counter reported for the four BASELINE models at 3x512x512 (prune.py:78; measured
+    in the build container) -- reproduced from shapes alone on the meta device."""
+    from dcfp_b200.pruners import flops
+    from dcfp_b200.workloads.segnets import CONFIGS, build_segnet
+    expected = {"c1": ("177.29 GFLOPs", "41.27 M"), "c2": ("255.19 GFLOPs", "60.26 M"), "c3": ("262.79 GFLOPs", "65.77 M"),
+                "c4": ("279.66 GFLOPs", "60.42 M")}
+    for cfg, exp in expected.items():
+        c = CONFIGS[cfg]
+        model = build_segnet(c["arch"], c["backbone"], c["num_classes"], seed=0, with_loss=False, deepsup=False)
+        assert flops.get_model_complexity_info(model, (3, 512, 512)) == exp, cfg
+
+
+def test_search_global_percent_oracle_backend():
+    """The FLOPs-ratio search stops at the first candidate under the target and its channel_cfg is the one prune_model
+    produces at that percent."""
+    from dcfp_b200.pruners.search import search_global_percent
+    model = gu.build_model("c1")
+    eic = gu.make_scores(model, "uniform", 31)
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".pth") as f:
+        torch.save({"eic": {k: torch.from_numpy(v) for k, v in eic.items()}}, f.name)
+        with oracle_backend():
+            gp, cfg_s, trace = search_global_percent(model, f.name, prune_ratio=0.62)
+            _, _, cfg_p = gu.run_product_prune(__import__("copy").deepcopy(model), eic, gp, 0.02)
+    ratios = [r for _, r in trace]
+    assert all(r > 0.38 for r in ratios[:-1]) and ratios[-1] <= 0.38 and len(trace) >= 3
+    assert [g for g, _ in trace][:3] == [0.5, 0.52, 0.54]
+    assert ratios == sorted(ratios, reverse=True)
+    for k in cfg_p:
+        assert cfg_p[k]["out_channels"] == cfg_s[k]["out_channels"] and cfg_p[k].get("in_channels") == cfg_s[k].get("in_channels")
+        assert np.array_equal(cfg_p[k]["out_mask"], cfg_s[k]["out_mask"])

@@ -135,3 +135,30 @@ def test_reference_prune_py_runs_unmodified_against_dropin(tmp_path):
     for k in ca:
         for kk, v in ca[k].items():
             assert np.array_equal(v, cb[k][kk]) if isinstance(v, np.ndarray) else v == cb[k][kk]
+    # the shape-only search (meta-device FLOPs, one K2 call per candidate, ONE gather for the winner) walks the same
+    # candidates, prints the same ratios and ends with the same pruned model as the reference's prune.py loop
+    from dcfp_b200.pruners.search import prune_to_flops_ratio, search_global_percent
+    with oracle_backend():
+        gp, cfg_s, trace = search_global_percent(copy.deepcopy(model), score, prune_ratio=0.45)
+        sub, cfg_p, gp2 = prune_to_flops_ratio(copy.deepcopy(model), score, prune_ratio=0.45)
+    ref_lines = [l for l in outs["reference"][0] if l.startswith("global_percent")]
+    assert ["global_percent: {}, flops_ratio: {}".format(g, r) for g, r in trace] == ref_lines
+    assert gp == gp2 and "global_percent: {},".format(gp) in ref_lines[-1]
+    sd = sub.state_dict()
+    assert list(sd.keys()) == list(a.keys()) and all(torch.equal(sd[k], a[k]) for k in a)
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c3", "c4"])
+def test_meta_flops_counter_equals_reference_counter(cfg):
+    """dcfp_b200.pruners.flops (forward on the meta device) vs utils/flops_counter.get_model_complexity_info."""
+    ref_compat.load_reference()
+    from utils.flops_counter import get_model_complexity_info as ref_info
+    from dcfp_b200.pruners import flops
+    model = gu.build_model(cfg)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exp = ref_info(model, (3, 256, 256), print_per_layer_stat=False, as_strings=False)
+        exp_s = ref_info(model, (3, 256, 256), print_per_layer_stat=False)
+    assert flops.model_cost(model, (3, 256, 256)) == exp
+    assert flops.get_model_complexity_info(model, (3, 256, 256)) == exp_s
