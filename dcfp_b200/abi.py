@@ -66,6 +66,7 @@ def load(path=LIB_PATH):
     lib.dcfp_channel_gather_workspace.argtypes = [i32]
     lib.dcfp_channel_gather_grouped.argtypes = [ctypes.POINTER(GatherDesc), i32, i32, vp, ctypes.c_size_t, vp]
     lib.dcfp_bias_comp.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    lib.dcfp_class_balance_weights.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32, ctypes.c_double, vp, vp, vp]
     _lib = lib
     return lib
 

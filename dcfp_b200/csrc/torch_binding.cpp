@@ -340,6 +340,29 @@ Tensor bias_comp(const Tensor& W, const Tensor& act) {
   return out;
 }
 
+// -> (weight fp64 [N,H,W], class_num int64 [N,K]); datasets/Base.py:73-89
+std::tuple<Tensor, Tensor> class_balance_weights(const Tensor& label, int64_t K, const optional<Tensor>& sample_class, int64_t mode,
+                                                 double beta, int64_t ignore_label) {
+  require_cuda(label, "label");
+  TORCH_CHECK(label.dim() == 3 && label.is_contiguous(), "dcfp::class_balance_weights: label must be contiguous [N,H,W]");
+  const int32_t* cls = nullptr;
+  if (sample_class.has_value()) {
+    require_cuda(*sample_class, "sample_class");
+    TORCH_CHECK(sample_class->scalar_type() == at::kInt && sample_class->is_contiguous() && sample_class->numel() == label.size(0),
+                "dcfp::class_balance_weights: sample_class must be int32 [N]");
+    cls = sample_class->data_ptr<int32_t>();
+  }
+  Tensor counts = at::empty({label.size(0), K + 1}, label.options().dtype(at::kLong));
+  Tensor weight = at::empty(label.sizes(), label.options().dtype(at::kDouble));
+  c10::cuda::CUDAGuard guard(label.device());
+  check_rc(dcfp_class_balance_weights(label.data_ptr(), label_dtype_of(label), static_cast<int>(label.size(0)),
+                                      static_cast<int>(label.size(1)), static_cast<int>(label.size(2)), static_cast<int>(K),
+                                      static_cast<int>(ignore_label), cls, static_cast<int>(mode), beta,
+                                      counts.data_ptr<int64_t>(), weight.data_ptr<double>(), cur_stream()),
+           "class_balance_weights");
+  return {weight, counts.slice(1, 0, K)};
+}
+
 int64_t launch_count(bool reset) { return dcfp_launch_count(reset ? 1 : 0); }
 int64_t abi_version() { return dcfp_abi_version(); }
 
@@ -365,6 +388,8 @@ TORCH_LIBRARY(dcfp, m) {
   m.def("channel_gather_grouped(Tensor[] srcs, Tensor[] out_idx, Tensor[] in_idx, int[] has_out, int[] has_in) -> Tensor[]",
         &channel_gather_grouped);
   m.def("bias_comp(Tensor W, Tensor act) -> Tensor", &bias_comp);
+  m.def("class_balance_weights(Tensor label, int K, Tensor? sample_class, int mode, float beta, int ignore_label) -> (Tensor, Tensor)",
+        &class_balance_weights);
   m.def("launch_count(bool reset) -> int", &launch_count);
   m.def("abi_version() -> int", &abi_version);
 }

@@ -77,6 +77,12 @@ def reduce_classes(S1):
     return load().reduce_classes(S1)
 
 
+def class_balance_weights(label, K, sample_class=None, mode=2, beta=0.9999, ignore_label=255):
+    """Per-pixel class-balance weights of the finetune data path (datasets/Base.py:73-89): -> (weight fp64 [N,H,W],
+    class_num int64 [N,K]).  mode 1: 1/(count+1); mode 2: effective-number ratio w.r.t. sample_class[n]."""
+    return load().class_balance_weights(label, int(K), sample_class, int(mode), float(beta), int(ignore_label))
+
+
 # ---- K2 ----------------------------------------------------------------------------------------
 def r_pair(r):
     """(float32(r), float32(1 - r)) exactly as `eic*r + g*(1-r)` sees them (dcfp_pruner.py:20)."""

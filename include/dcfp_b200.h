@@ -154,6 +154,15 @@ int dcfp_channel_gather_grouped(const dcfp_gather_desc* descs_host, int n, int e
  * offset[o] = sum_i act[i] * sum_e W[o, i, e]   (fp32; act = relu((1 - in_mask) * beta_parent)) */
 int dcfp_bias_comp(const float* W, int O, int I, int khw, const float* act, float* offset_out, void* stream);
 
+/* ---- class-balance pixel weights -- datasets/Base.py:73-89 (get_label; finetune stage) ------------------
+ * class_num[n][k] (k < K; bin K = ignore label) = per-image pixel counts; weight[n][p] (float64, as numpy) =
+ * clip(w[label], 0, 1) with w = 1/(class_num+1) (mode 1) or the effective-number ratio
+ * (1 + 1e-8 - beta^class_num[sample_class[n]]) / (1 + 1e-8 - beta^class_num[k]) (mode 2); ignored pixels get 0.
+ * class_num: device [N][K+1] int64 (overwritten); sample_class: device [N] int32 (mode 2) or NULL.            */
+int dcfp_class_balance_weights(const void* label, int label_dtype, int N, int H, int W, int K, int ignore_label,
+                               const int32_t* sample_class, int mode, double beta, int64_t* class_num, double* weight,
+                               void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------- */
 const char* dcfp_last_error(void);
 int dcfp_abi_version(void);

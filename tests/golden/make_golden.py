@@ -3,7 +3,7 @@
 Run in the build container only (needs /root/reference; oracle/ref_compat.py holds the three
 arithmetic-free shims):
 
-    python tests/golden/make_golden.py [eic] [prune] [scoring] [sweep]
+    python tests/golden/make_golden.py [eic] [prune] [scoring] [sweep] [balance]
 
 The reference ships no tests or golden vectors, so these files ARE the pin of the oracle and of the
 CUDA path on the GPU box, where /root/reference does not exist.
@@ -16,6 +16,7 @@ CUDA path on the GPU box, where /root/reference does not exist.
   prune_c1_beta.npz    same with non-zero BN beta -> exercises bias compensation (channel_pruner.py:873-905);
                        stores the compensated running_mean vectors (fp32 GEMV: compared with a tolerance)
   sweep_c{1,3}.npz     thresholds + raw keep masks for all 25 global_percent values prune.py can visit
+  balance.npz          BaseDataSet.get_label (datasets/Base.py:73-89): class-balance pixel weights, modes 1 and 2
   scoring_small.npz    reference Seg_Model + CriterionDSN + dcfp_pruning over 2 steps on 2x3x64x128 inputs:
                        per-step BN-gamma gradients and the final EIC (pins oracle/scoring_ref.py)
 """
@@ -268,6 +269,35 @@ def gen_sweep():
         print("wrote sweep_%s.npz (%d percents, %d links)" % (cfg_name, len(meta["percents"]), len(meta["links"])))
 
 
+def gen_balance():
+    """BaseDataSet.get_label (datasets/Base.py:73-89), the reference's own method called unbound on a stand-in `self`."""
+    ref_compat.load_reference()
+    import types
+    import importlib.util  # `datasets` on sys.path is the Hugging Face package: load the reference's file by path
+    spec = importlib.util.spec_from_file_location("dcfp_ref_datasets_base", os.path.join(ref_compat.REF_ROOT, "datasets", "Base.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    BaseDataSet = mod.BaseDataSet
+    from dcfp_b200.workloads.synthetic import synthetic_labels
+    out = {}
+    cases = []
+    for ci, (K, H, W, balance, beta) in enumerate([(19, 96, 160, 2, 0.9999), (19, 96, 160, 1, 0.9999), (150, 64, 64, 2, 0.9999),
+                                                   (171, 80, 48, 2, 0.999)]):
+        for img in range(3):
+            label = synthetic_labels(100 * ci + img, K, H, W).numpy()
+            present = np.unique(label[label != 255])
+            cls = int(present[(7 * img) % len(present)])
+            this = types.SimpleNamespace(balance=balance, ignore_label=255, num_classes=K, beta=beta)
+            res = BaseDataSet.get_label(this, label, {"class": cls})
+            assert res["weight"].dtype == np.float64 and np.array_equal(res["ori"], label)
+            out["label_%d_%d" % (ci, img)] = label
+            out["weight_%d_%d" % (ci, img)] = res["weight"]
+            cases.append(dict(case=ci, img=img, K=K, balance=balance, beta=beta, sample_class=cls))
+    out["meta"] = np.frombuffer(json.dumps(cases).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "balance.npz"), **out)
+    print("wrote balance.npz (%d images)" % len(cases))
+
+
 def gen_scoring():
     """Reference model + loss + dcfp_pruning, the restated loop of train.py:255-268, tiny inputs."""
     ref = ref_compat.load_reference()
@@ -299,12 +329,14 @@ def gen_scoring():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["eic", "prune", "scoring", "sweep"]
+    what = sys.argv[1:] or ["eic", "prune", "scoring", "sweep", "balance"]
     assert ref_compat.available(), "reference tree not found"
     if "eic" in what:
         gen_eic()
     if "scoring" in what:
         gen_scoring()
+    if "balance" in what:
+        gen_balance()
     if "sweep" in what:
         gen_sweep()
     if "prune" in what or "beta" in what:

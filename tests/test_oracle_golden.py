@@ -103,3 +103,21 @@ def test_scoring_restatement_matches_reference_run():
         assert flipped.mean() <= 0.01, "%s: %d of %d channels differ" % (n, flipped.sum(), flipped.size)
     after = model.state_dict()
     assert all(torch.equal(before[k], after[k]) for k in before), "scoring must leave the model untouched"
+
+
+def _balance_cases():
+    import json
+    z = np.load(os.path.join(GOLDEN, "balance.npz"))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+def test_class_balance_restatement_matches_reference_bits():
+    """oracle/balance_ref.py vs BaseDataSet.get_label of the reference (datasets/Base.py:73-89): float64, bit-exact."""
+    from oracle import balance_ref
+    z, cases = _balance_cases()
+    for c in cases:
+        label = z["label_%d_%d" % (c["case"], c["img"])]
+        w, cnt = balance_ref.class_balance_weights(label, c["K"], c["sample_class"], c["balance"], c["beta"])
+        exp = z["weight_%d_%d" % (c["case"], c["img"])]
+        assert w.dtype == np.float64 and np.array_equal(w.view(np.uint64), exp.view(np.uint64)), c
+        assert cnt.sum() == (label != 255).sum()
