@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
   // slot cache: lane i (< kNhwcSlots) holds the class of row i (kFree = none); round-robin victim; last hit
   constexpr unsigned kFree = 0xffffffffu;
-  unsigned my_tag = kFree;
+  unsigned my_tag = kFree, used = 0;  // `used`: CLOCK reference bits of the rows (warp-uniform)
   int victim = 0;
   unsigned last_key = 0xffffffffu;
   int last_slot = 0;
@@ -561,9 +561,17 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     int slot;
     if (hit) {
       slot = __ffs(hit) - 1;
+      used |= 1u << slot;
     } else {
-      slot = victim;
-      victim = victim + 1 == kNhwcSlots ? 0 : victim + 1;
+      // CLOCK replacement: take the first row (from the hand) not referenced since the hand last passed it, so the
+      // classes of the rows being streamed stay resident while stale ones leave (round-robin evicted hot rows)
+      constexpr unsigned kAll = (1u << kNhwcSlots) - 1u;
+      if ((used & kAll) == kAll) used = 0;
+      const unsigned cand = ~used & kAll;
+      const unsigned ahead = cand & ~((1u << victim) - 1u);
+      slot = __ffs(ahead ? ahead : cand) - 1;
+      victim = slot + 1 == kNhwcSlots ? 0 : slot + 1;
+      used |= 1u << slot;
       const unsigned old = __shfl_sync(0xffffffffu, my_tag, slot);
       if (old != kFree) row_to_arena(slot, old);
       if (lane == slot) my_tag = cls;
@@ -609,6 +617,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       }
       my_tag = kFree;
       victim = 0;
+      used = 0;
       last_key = 0xffffffffu;
     }
   };
