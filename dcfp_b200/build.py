@@ -49,7 +49,7 @@ def _run(cmd, verbose):
 def build_abi(force=False, verbose=False, ptxas_verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in CU_SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "dcfp_b200.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(INCLUDE, "dcfp_b200.h")]
     if not force and not _stale(ABI_LIB, deps):
         return ABI_LIB
     objs = []

@@ -1,0 +1,537 @@
+// K1, channels_last feature maps: TMA [G pixels x 128 channels] boxes, lane = 4 channels, per-warp slot cache.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+
+#include "k1_common.cuh"
+
+namespace dcfp {
+namespace {
+
+// ---- channels_last (NHWC) path ---------------------------------------------------------------------
+// x[n][p][c] with C contiguous: every pixel has ONE class for all its channels, so with lane = 4 consecutive
+// channels the class key is warp-uniform by construction and a pixel's [128-channel slab] is read straight out of
+// a TMA-staged box with one conflict-free LDS per lane -- no transposition.
+//  * Each warp owns a slab and a pixel phase and runs a private 2-stage pipeline of [G pixels x 128 channels]
+//    tensor-tile copies (cp.async.bulk.tensor.2d, mbarrier completion, evict-first): the bytes in flight live in
+//    shared memory, not in registers or L1 miss queues (a register-staged LDG version of this kernel stalled at
+//    56 % of the roofline with the same nominal bytes in flight).
+//  * Accumulation is STATE-FREE straight-line code: the 8 pixel rows of one 64-bit key word (or the 4 of a quad, or
+//    a single straddling pixel) are summed in registers and added to the class's row.  Carrying an open run in
+//    registers across pixels made ptxas shuffle the accumulators at every possible run boundary (29 instructions
+//    per pixel row, 23 % of them moves) and left 8 warps/SM issue-latency bound at half the roofline.
+//  * Rows live in the warp's private SLOT CACHE: 12 rows of [2][128] fp32; the class held by row i is a register
+//    of lane i, looked up with one ballot (fully associative).  Labels are spatially coherent, so a warp meets few
+//    classes at a time; a 13th class evicts a row to the fp64 arena.  12 KB per warp for ANY K <= 255: no table
+//    sized by K, no shared atomics, no CTA-wide barrier anywhere.
+//  * Class keys are fetched 32 iterations at a time (lane j holds iteration block + j) and broadcast by shuffle:
+//    a per-iteration global load put ~1 us on every iteration's critical path.
+//  * The kernel is PERSISTENT (one CTA per SM walks a contiguous range of tiles ordered (layer, slab group,
+//    chunk)); rows are folded into the arena only when the (layer, slab group) changes.
+// cuDNN's tensor-core convolutions are NHWC-native: running the feature-map producer in channels_last removes its
+// layout transposes (measured 52 -> 36 ms per c2 step) -- this is the layout bench.py scores.
+constexpr int kNhwcWarps = 8;
+constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
+constexpr int kNhwcSlots = 12;       // class rows per warp (tag of row i lives in lane i)
+// one staged box = [G px][128 ch]: 8 KB forward (G = 16 fp32 / 32 bf16), 4 KB per tensor backward (x and dy boxes):
+// 8 KB per pipeline stage either way, so the fixed per-iteration work (wait, key broadcast, refill) is paid per 8 KB
+__host__ __device__ constexpr int nhwc_box_bytes(bool bwd) { return bwd ? 4096 : 8192; }
+
+struct NhwcLayer {
+  const uint8_t* keys;  // [N*HW]
+  const float* scale;
+  const float* shift;
+  double* S1;
+  double* S2;
+  int32_t C, ld, centered;  // C: columns of the [rows][C] view the tensor map describes
+  int32_t n_px;           // rows of that view: N * HW, or N * HW / 2 when fold2
+  int32_t fold2;          // 64-channel layer viewed as [N*HW/2][128]: a row = 2 pixels, lanes 16-31 hold the odd one
+  int32_t spc;            // slabs per CTA: 1, 2, 4 or 8
+  int32_t n_slab_groups;  // ceil(ceil(C / 128) / spc)
+  int32_t px_per_chunk;   // multiple of G * (8 / spc)
+  int32_t n_chunks;
+};
+template <int MAXL, int TENS>
+struct NhwcParams {
+  alignas(64) CUtensorMap maps[MAXL * TENS];  // [layer][x, dy]: [n_px rows][C cols], box [G][128]
+  NhwcLayer L[MAXL];
+  int32_t tile_prefix[MAXL + 1];
+  int32_t n_layers;
+  int32_t K;
+  int32_t stages;  // boxes in flight per warp
+};
+constexpr int kNhwcBigGroupFwd = 128;  // 128 * (128 + 72) B = 25.0 KB of kernel parameters
+constexpr int kNhwcBigGroupBwd = 80;   //  80 * (256 + 72) B = 25.6 KB
+
+// the lane's 4 channels of pixel `row` inside a staged box, as two packed fp32 pairs
+template <typename T>
+struct BoxRow;
+template <>
+struct BoxRow<float> {
+  static constexpr int kRowBytes = kNhwcSlab * 4;
+  __device__ static __forceinline__ void load(uint32_t box_lane, int row, f2& a, f2& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(box_lane + row * (kNhwcSlab * 4)));
+  }
+  static constexpr int kLaneBytes = 16;
+};
+template <>
+struct BoxRow<__nv_bfloat16> {
+  static constexpr int kRowBytes = kNhwcSlab * 2;
+  __device__ static __forceinline__ void load(uint32_t box_lane, int row, f2& a, f2& b) {
+    unsigned lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(box_lane + row * (kNhwcSlab * 2)));
+    a = Elem<__nv_bfloat16>::widen(lo);
+    b = Elem<__nv_bfloat16>::widen(hi);
+  }
+  static constexpr int kLaneBytes = 8;
+};
+
+constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-boxes, or 2 (x, dy) pairs
+
+template <typename T, bool BWD, bool AFFINE, int MAXL>
+__global__ void __launch_bounds__(kNhwcWarps * 32, 1)
+    class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P) {
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD);
+  constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
+  constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
+  constexpr int kTens = BWD ? 2 : 1;
+  constexpr int kStageBytes = kTens * kNhwcBoxBytes;
+  const int kStages = P.stages;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // [warp][stage][x | dy] boxes | [warp][slot][2][128] fp32 | [warp][stage] mbarriers
+  float* slots = reinterpret_cast<float*>(smem + kNhwcWarps * kStages * kStageBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(slots + kNhwcWarps * kNhwcSlots * 256);
+
+  const unsigned K = static_cast<unsigned>(P.K);
+  const int n_tiles = P.tile_prefix[P.n_layers];
+  const int t_first = static_cast<int>(static_cast<long long>(blockIdx.x) * n_tiles / gridDim.x);
+  const int t_last = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_tiles / gridDim.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* const mine = reinterpret_cast<float4*>(slots + static_cast<size_t>(warp) * kNhwcSlots * 256) + lane;
+  const uint32_t my_bufs = smem_u32(smem + static_cast<size_t>(warp) * kStages * kStageBytes);
+  const uint32_t my_bars = smem_u32(&bars[warp * kStages]);
+  const uint32_t lane_off = static_cast<uint32_t>(lane * BoxRow<T>::kLaneBytes);
+  const unsigned dropped = K * 0x01010101u;
+  const bool direct = K <= static_cast<unsigned>(kNhwcSlots);  // slot == class, no tags
+  const uint64_t policy = policy_evict_first();
+
+  if (lane < kStages) mbar_init(my_bars + lane * 8, 1);
+  for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  mbar_fence_init();
+  __syncwarp();
+  unsigned parity_bits = 0;  // bit s = parity of the next completion of stage s
+
+  int layer = 0, cur_layer = -1, cur_sg = -1;
+  int phases = kNhwcWarps, phase = 0, c0 = 0, col0 = 0;
+  bool lane_on = false, fold2 = false;
+  double* out1 = nullptr;  // &S1[c0], &S2[c0] of the current layer
+  double* out2 = nullptr;
+  size_t ld = 0;
+  f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
+  // slot cache: lane i (< kNhwcSlots) holds the class of row i (kFree = none); round-robin victim; last hit
+  constexpr unsigned kFree = 0xffffffffu;
+  unsigned my_tag = kFree, used = 0;  // `used`: CLOCK reference bits of the rows (warp-uniform)
+  int victim = 0;
+  unsigned last_key = 0xffffffffu;
+  int last_slot = 0;
+  const uint32_t mine_u32 = smem_u32(mine);
+
+  auto row_to_arena = [&](int slot, unsigned cls) {  // fp32 row -> fp64 arena, row zeroed
+    const float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
+    if (lane_on) {
+      double* d1 = out1 + cls * ld;
+      double* d2 = out2 + cls * ld;
+      if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));
+      if (a.y != 0.f) atomicAdd(d1 + 1, static_cast<double>(a.y));
+      if (a.z != 0.f) atomicAdd(d1 + 2, static_cast<double>(a.z));
+      if (a.w != 0.f) atomicAdd(d1 + 3, static_cast<double>(a.w));
+      if (b.x != 0.f) atomicAdd(d2 + 0, static_cast<double>(b.x));
+      if (b.y != 0.f) atomicAdd(d2 + 1, static_cast<double>(b.y));
+      if (b.z != 0.f) atomicAdd(d2 + 2, static_cast<double>(b.z));
+      if (b.w != 0.f) atomicAdd(d2 + 3, static_cast<double>(b.w));
+    }
+    mine[slot * 64] = make_float4(0.f, 0.f, 0.f, 0.f);
+    mine[slot * 64 + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto slot_of = [&](unsigned cls) -> int {  // warp-uniform
+    if (direct) return static_cast<int>(cls);
+    if (cls == last_key) return last_slot;
+    const unsigned hit = __ballot_sync(0xffffffffu, my_tag == cls);  // fully associative lookup in one vote
+    int slot;
+    if (hit) {
+      slot = __ffs(hit) - 1;
+      used |= 1u << slot;
+    } else {
+      // CLOCK replacement: take the first row (from the hand) not referenced since the hand last passed it, so the
+      // classes of the rows being streamed stay resident while stale ones leave (round-robin evicted hot rows)
+      constexpr unsigned kAll = (1u << kNhwcSlots) - 1u;
+      if ((used & kAll) == kAll) used = 0;
+      const unsigned cand = ~used & kAll;
+      const unsigned ahead = cand & ~((1u << victim) - 1u);
+      slot = __ffs(ahead ? ahead : cand) - 1;
+      victim = slot + 1 == kNhwcSlots ? 0 : slot + 1;
+      used |= 1u << slot;
+      const unsigned old = __shfl_sync(0xffffffffu, my_tag, slot);
+      if (old != kFree) row_to_arena(slot, old);
+      if (lane == slot) my_tag = cls;
+    }
+    last_key = cls;
+    last_slot = slot;
+    return slot;
+  };
+  // row[class] += (sum, sum of squares) of this lane's 4 channels over a few pixels of one class.  No run state is
+  // carried between pixel groups: every path below is straight-line code over values that die at the row update.
+  auto row_add = [&](unsigned key, f2 s1a, f2 s1b, f2 s2a, f2 s2b) {
+    if (key >= K) return;  // dropped pixels (warp-uniform)
+    const uint32_t addr = mine_u32 + static_cast<uint32_t>(slot_of(key)) * 1024u;
+    f2 a, b, c, d;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(c), "=l"(d) : "r"(addr + 512u));
+    a = add2(a, s1a);
+    b = add2(b, s1b);
+    c = add2(c, s2a);
+    d = add2(d, s2b);
+    asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+    asm volatile("st.shared.v2.b64 [%0], {%1,%2};" ::"r"(addr + 512u), "l"(c), "l"(d) : "memory");
+  };
+  auto load_px = [&](uint32_t box_lane, int row, f2& a, f2& b) {  // value functor of one pixel row
+    BoxRow<T>::load(box_lane, row, a, b);
+    if (BWD) {
+      f2 da, db;
+      BoxRow<T>::load(box_lane + kNhwcBoxBytes, row, da, db);
+      a = mul2(da, fma2(a, sc01, sf01));
+      b = mul2(db, fma2(b, sc23, sf23));
+    } else if (AFFINE) {
+      a = fma2(a, sc01, sf01);
+      b = fma2(b, sc23, sf23);
+    }
+  };
+  auto fold = [&]() {  // every row of this warp -> arena (end of a (layer, slab group))
+    if (direct) {
+      for (unsigned k = 0; k < K; ++k) row_to_arena(static_cast<int>(k), k);
+    } else {
+      for (int slot = 0; slot < kNhwcSlots; ++slot) {
+        const unsigned cls = __shfl_sync(0xffffffffu, my_tag, slot);
+        if (cls != kFree) row_to_arena(slot, cls);
+      }
+      my_tag = kFree;
+      victim = 0;
+      used = 0;
+      last_key = 0xffffffffu;
+    }
+  };
+
+  for (int tile = t_first; tile < t_last; ++tile) {
+    while (tile >= P.tile_prefix[layer + 1]) ++layer;
+    const NhwcLayer& L = P.L[layer];
+    const CUtensorMap* maps = &P.maps[layer * kTens];
+    const int t = tile - P.tile_prefix[layer];
+    const int sg = t / L.n_chunks;
+    const int chunk = t - sg * L.n_chunks;
+    if (layer != cur_layer || sg != cur_sg) {
+      if (cur_layer >= 0) fold();
+      cur_layer = layer;
+      cur_sg = sg;
+      const int spc = L.spc;
+      phases = kNhwcWarps / spc;
+      phase = warp / spc;
+      col0 = (sg * spc + warp % spc) * kNhwcSlab;
+      c0 = col0 + lane * 4;
+      lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside (TMA zero-fills outside)
+      fold2 = L.fold2 != 0;
+      if (fold2) c0 &= 63;  // columns 64..127 of a pixel-pair row are channels 0..63 of the odd pixel
+      ld = static_cast<size_t>(L.ld);
+      out1 = L.S1 + c0;
+      out2 = L.S2 + c0;
+      sc01 = sc23 = pack2(1.f, 1.f);
+      sf01 = sf23 = 0;
+      if (lane_on && (BWD || AFFINE)) {
+        float sc[4], sf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc[j] = L.scale ? L.scale[c0 + j] : 1.f;
+          sf[j] = L.shift ? L.shift[c0 + j] : 0.f;
+          if (L.centered) sf[j] = -sf[j] * sc[j];
+        }
+        sc01 = pack2(sc[0], sc[1]);
+        sc23 = pack2(sc[2], sc[3]);
+        sf01 = pack2(sf[0], sf[1]);
+        sf23 = pack2(sf[2], sf[3]);
+      }
+    }
+
+    const int p_begin = chunk * L.px_per_chunk;
+    const int p_end = min(p_begin + L.px_per_chunk, L.n_px);
+    const int n_groups = (p_end - p_begin + G - 1) / G;
+    const int n_my = col0 < L.C ? (n_groups - phase + phases - 1) / phases : 0;  // a warp whose slab is empty idles
+
+    int issue_it = 0, issue_stage = 0;
+    auto issue = [&]() {  // one elected lane arms the barrier and launches the tile copies of the warp's next group
+      if (issue_it < n_my) {
+        if (lane == 0) {
+          const uint32_t bar = my_bars + issue_stage * 8;
+          const uint32_t dst = my_bufs + issue_stage * kStageBytes;
+          const int p = p_begin + (phase + issue_it * phases) * G;
+          mbar_expect_tx(bar, kStageBytes);
+          tma_load_2d(dst, maps, col0, p, bar, policy);  // rows past n_px / columns past C arrive as zeros
+          if (BWD) tma_load_2d(dst + kNhwcBoxBytes, maps + 1, col0, p, bar, policy);
+        }
+      }
+      ++issue_it;
+      if (++issue_stage == kStages) issue_stage = 0;
+    };
+    // Class keys: lane j holds the packed keys of the warp's iteration (block + j), fetched 32 iterations at a time
+    // and one block ahead, then broadcast with a shuffle.  (A per-iteration global load -- even issued one iteration
+    // early -- put its full latency on every iteration's critical path: 8 warps/SM cannot hide ~1 us per 4 KB box.)
+    const int kf = fold2 ? 2 : 1;  // key bytes per row
+    auto fetch_keys = [&](int it0, unsigned* dst) {
+      const int it = it0 + lane;
+#pragma unroll
+      for (int q = 0; q < 2 * Q; ++q) dst[q] = dropped;
+      if (it < n_my) {
+        const int p = p_begin + (phase + it * phases) * G;
+        if (p + G <= p_end) {
+#pragma unroll
+          for (int q = 0; q < 2 * Q; ++q)
+            if (q < Q * kf) dst[q] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(p) * kf) + q) : 0u;
+        } else {  // ragged tail of the chunk: missing pixels are "dropped"
+#pragma unroll
+          for (int i = 0; i < 2 * G; ++i) {
+            if (i < G * kf && p * kf + i < p_end * kf) {
+              const unsigned k = L.keys ? L.keys[static_cast<size_t>(p) * kf + i] : 0u;
+              const int sh = 8 * (i & 3);
+              dst[i >> 2] = (dst[i >> 2] & ~(0xffu << sh)) | (k << sh);
+            }
+          }
+        }
+      }
+    };
+    unsigned kcur[2 * Q], knxt[2 * Q], kw[2 * Q];
+    fetch_keys(0, kcur);
+    fetch_keys(32, knxt);
+
+    for (int s = 0; s < kStages; ++s) issue();
+    int stage = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int j = it & 31;
+      if (j == 0 && it > 0) {
+#pragma unroll
+        for (int q = 0; q < 2 * Q; ++q) kcur[q] = knxt[q];
+        fetch_keys(it + 32, knxt);
+      }
+#pragma unroll
+      for (int q = 0; q < 2 * Q; ++q)
+        if (q < Q * kf) kw[q] = __shfl_sync(0xffffffffu, kcur[q], j);
+      mbar_wait(my_bars + stage * 8, (parity_bits >> stage) & 1u);
+      parity_bits ^= 1u << stage;
+      const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
+      if (fold2) {
+        // pixel-pair rows: row r = pixels 2r (lanes 0-15) and 2r+1 (lanes 16-31); 8 rows = 16 key bytes = 4 words
+        const bool upper = lane >= 16;
+#pragma unroll
+        for (int hf = 0; hf < G / 8; ++hf) {
+          const unsigned w0 = kw[4 * hf], w1 = kw[4 * hf + 1], w2 = kw[4 * hf + 2], w3 = kw[4 * hf + 3];
+          const unsigned k0 = w0 & 0xffu;
+          if (w0 == k0 * 0x01010101u && w1 == w0 && w2 == w0 && w3 == w0) {  // 16 pixels of one class
+            f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f2 a, b;
+              load_px(box_lane, 8 * hf + e, a, b);
+              s1a = add2(s1a, a);
+              s1b = add2(s1b, b);
+              s2a = fma2(a, a, s2a);
+              s2b = fma2(b, b, s2b);
+            }
+            row_add(k0, s1a, s1b, s2a, s2b);
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {  // 4 rows = 8 pixels = 2 key words
+              const unsigned wa = q ? w2 : w0, wb = q ? w3 : w1;
+              const unsigned kq = wa & 0xffu;
+              const int row0 = 8 * hf + 4 * q;
+              if (wa == kq * 0x01010101u && wb == wa) {
+                f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f2 a, b;
+                  load_px(box_lane, row0 + e, a, b);
+                  s1a = add2(s1a, a);
+                  s1b = add2(s1b, b);
+                  s2a = fma2(a, a, s2a);
+                  s2b = fma2(b, b, s2b);
+                }
+                row_add(kq, s1a, s1b, s2a, s2b);
+              } else {
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) {  // one row: its two pixels may belong to two classes
+                  const unsigned pair = ((e < 2 ? wa : wb) >> (16 * (e & 1))) & 0xffffu;
+                  const unsigned ke = pair & 0xffu, ko = pair >> 8;
+                  f2 a, b;
+                  load_px(box_lane, row0 + e, a, b);
+                  if (ke == ko) {
+                    row_add(ke, a, b, mul2(a, a), mul2(b, b));
+                  } else {  // even pixel: lanes 0-15 contribute, odd pixel: lanes 16-31
+                    const f2 ae = upper ? 0 : a, be = upper ? 0 : b, ao = upper ? a : 0, bo = upper ? b : 0;
+                    row_add(ke, ae, be, mul2(ae, ae), mul2(be, be));
+                    row_add(ko, ao, bo, mul2(ao, ao), mul2(bo, bo));
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+      for (int hf = 0; hf < G / 8; ++hf) {  // 8 pixels = one 64-bit key word at a time
+        const unsigned w_lo = kw[2 * hf], w_hi = kw[2 * hf + 1];
+        const unsigned k0 = w_lo & 0xffu;
+        if (w_lo == k0 * 0x01010101u && w_hi == w_lo) {  // one class: 8 rows summed in registers, one row update
+          f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f2 a, b;
+            load_px(box_lane, 8 * hf + e, a, b);
+            s1a = add2(s1a, a);
+            s1b = add2(s1b, b);
+            s2a = fma2(a, a, s2a);
+            s2b = fma2(b, b, s2b);
+          }
+          row_add(k0, s1a, s1b, s2a, s2b);
+        } else {  // a class boundary inside: per quad, and pixel by pixel only in the quad that straddles it
+#pragma unroll 1
+          for (int q = 0; q < 2; ++q) {
+            const unsigned w = q ? w_hi : w_lo;
+            const unsigned kq = w & 0xffu;
+            const int row0 = 8 * hf + 4 * q;
+            if (w == kq * 0x01010101u) {
+              f2 s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f2 a, b;
+                load_px(box_lane, row0 + e, a, b);
+                s1a = add2(s1a, a);
+                s1b = add2(s1b, b);
+                s2a = fma2(a, a, s2a);
+                s2b = fma2(b, b, s2b);
+              }
+              row_add(kq, s1a, s1b, s2a, s2b);
+            } else {
+#pragma unroll 1
+              for (int e = 0; e < 4; ++e) {
+                f2 a, b;
+                load_px(box_lane, row0 + e, a, b);
+                row_add((w >> (8 * e)) & 0xffu, a, b, mul2(a, a), mul2(b, b));
+              }
+            }
+          }
+        }
+      }
+      }  // !fold2
+      __syncwarp();
+      issue();  // refill the stage just consumed
+      if (++stage == kStages) stage = 0;
+    }
+  }
+  if (cur_layer >= 0) fold();
+}
+
+// NHWC: [rows = N*HW][cols = C], box = [G px][128 channels], no swizzle (a pixel row is read with one LDS per lane)
+int make_map_nhwc(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols, int box_bytes) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  DCFP_REQUIRE(enc != nullptr, DCFP_EUNSUPPORTED, "class_stats: cuTensorMapEncodeTiled is not available in this driver");
+  const size_t es = dtype == DCFP_F32 ? 4 : 2;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * es};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kNhwcSlab), static_cast<cuuint32_t>(box_bytes / (kNhwcSlab * es))};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(map, dtype == DCFP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCFP_REQUIRE(r == CUDA_SUCCESS, DCFP_EINVAL, "class_stats: cuTensorMapEncodeTiled (NHWC) failed (CUresult %d) rows=%lld cols=%lld",
+               static_cast<int>(r), rows, cols);
+  return 0;
+}
+
+// the NHWC fast path (TMA): 16-B aligned base and row pitch, whole 4-channel vectors
+bool nhwc_ok(const dcfp_layer_desc& d) {
+  if (d.layout != DCFP_NHWC) return false;
+  const size_t es = d.dtype == DCFP_F32 ? 4 : 2;
+  if (d.C % 4 != 0 || (static_cast<size_t>(d.C) * es) % 16 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(d.x) % 16 != 0) return false;
+  if (d.dy && reinterpret_cast<uintptr_t>(d.dy) % 16 != 0) return false;
+  if (d.keys && reinterpret_cast<uintptr_t>(d.keys) % 4 != 0) return false;
+  if (static_cast<long long>(d.N) * d.h * d.w < 64) return false;  // tiny pooled maps: generic
+  return true;
+}
+
+template <typename T, bool BWD, int MAXL>
+int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long target_bytes, cudaStream_t stream) {
+  constexpr int kTens = BWD ? 2 : 1;
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD);
+  constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
+  const int K = descs[which[0]].K;
+  NhwcParams<MAXL, kTens> P;
+  P.n_layers = n;
+  P.K = K;
+  P.tile_prefix[0] = 0;
+  bool affine = false;
+  for (int i = 0; i < n; ++i) {
+    const dcfp_layer_desc& d = descs[which[i]];
+    NhwcLayer& L = P.L[i];
+    affine = affine || d.scale || d.shift;
+    L.keys = d.keys;
+    L.scale = d.scale;
+    L.shift = d.shift;
+    L.S1 = d.S1;
+    L.S2 = d.S2;
+    L.C = d.C;
+    L.ld = d.ld > 0 ? d.ld : d.C;
+    L.centered = d.affine_mode == DCFP_AFFINE_INVSTD_MEAN;
+    L.n_px = d.N * d.h * d.w;
+    // a 64-channel layer fills only half of a 128-channel slab: view it as [n_px / 2][128] (pixel-pair rows)
+    L.fold2 = (d.C == 64 && L.n_px % 2 == 0) ? 1 : 0;
+    if (L.fold2) {
+      L.C = 128;
+      L.n_px /= 2;
+    }
+    const int n_slabs = (L.C + kNhwcSlab - 1) / kNhwcSlab;
+    int spc = 1;
+    while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
+    L.spc = spc;
+    L.n_slab_groups = (n_slabs + spc - 1) / spc;
+    const int gran = G * (kNhwcWarps / spc);  // every phase gets whole pixel groups
+    const long long row_bytes = static_cast<long long>(std::min(L.C, spc * kNhwcSlab)) * sizeof(T);
+    long long px = std::max<long long>(target_bytes / row_bytes, gran);
+    px = (px + gran - 1) / gran * gran;
+    L.px_per_chunk = static_cast<int>(std::min<long long>(px, (static_cast<long long>(L.n_px) + gran - 1) / gran * gran));
+    L.n_chunks = (L.n_px + L.px_per_chunk - 1) / L.px_per_chunk;
+    const long long tiles = static_cast<long long>(L.n_chunks) * L.n_slab_groups;
+    DCFP_REQUIRE(P.tile_prefix[i] + tiles < (1LL << 31), DCFP_ETOOBIG, "class_stats: too many tiles");
+    P.tile_prefix[i + 1] = P.tile_prefix[i] + static_cast<int>(tiles);
+    int rc = make_map_nhwc(&P.maps[i * kTens], d.x, d.dtype, L.n_px, L.C, kNhwcBoxBytes);
+    if (rc == 0 && BWD) rc = make_map_nhwc(&P.maps[i * kTens + 1], d.dy, d.dtype, L.n_px, L.C, kNhwcBoxBytes);
+    if (rc) return rc;
+  }
+  const int n_tiles = P.tile_prefix[n];
+  if (n_tiles == 0) return 0;
+  static const int forced = []() {
+    const char* e = getenv("DCFP_K1_NHWC_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  P.stages = kNhwcStageBudget / (kTens * kNhwcBoxBytes);
+  if (forced >= 1 && forced * kTens * kNhwcBoxBytes <= (20 << 10)) P.stages = forced;
+  const size_t smem = static_cast<size_t>(kNhwcWarps) * P.stages * kTens * kNhwcBoxBytes +
+                      static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float) + 8 * kNhwcWarps * P.stages +
+                      1024 /* base alignment slack */;
+  void (*kern)(NhwcParams<MAXL, kTens>) = class_stats_nhwc_kernel<T, BWD, true, MAXL>;
+  if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL>;
+  int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
+  if (rc) return rc;
+  kern<<<std::min(n_tiles, kNumSMs), kNhwcWarps * 32, smem, stream>>>(P);  // persistent: one CTA per SM
+  return finish_launch("class_stats_nhwc");
+}
+
+}  // namespace
+}  // namespace dcfp
