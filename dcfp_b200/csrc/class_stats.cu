@@ -1,31 +1,18 @@
-// K1 -- label-keyed segmented reduction over conv/BN feature maps (sm_100a).
+// K1 -- label-keyed segmented reduction over conv/BN feature maps (sm_100a): dispatcher, generic kernel, label keys.
 //
 //   S1[k][c] += sum_{pixels p of class k} v(p, c),      S2[k][c] += sum v(p, c)^2
 //
-// HBM-bound: every feature-map byte is read exactly once; there is no dense contraction, so no
-// tensor cores.  Design:
+// HBM-bound: every feature-map byte is read exactly once; there is no dense contraction, so no tensor cores.
+// Design:
 //
-//  * `dcfp_label_keys` nearest-down-samples the label map in registers ONCE per label resolution
-//    into a compact uint8 class-key plane (and counts pixels per class).  Doing it inside the
-//    reduction was measured at 27 % of all issued instructions, repeated by every 32-channel
-//    group of every layer (profiles/r01_k1_notes.md).
-//  * NCHW planes are pixel-contiguous, but the class key varies along pixels and is identical
-//    across channels.  Each warp therefore pulls [32 channels x 128 B] boxes into shared memory
-//    with ONE TMA tensor-tile copy (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier completion)
-//    and reads them back TRANSPOSED -- lane == channel -- with conflict-free 128-bit loads.  The
-//    class key of every pixel is then warp-uniform.
-//  * With a warp-uniform key the reduction is a run-length accumulate in registers (packed
-//    FADD2/FFMA2): while the key does not change, a1 += v, a2 += v*v; on a change the run is
-//    flushed to a [K x 32] accumulator in shared memory.  A box whose 32/64 keys all equal the
-//    current run's takes a branch-free path.
-//  * Every warp owns a private multi-stage pipeline (its own mbarriers): the main loop has no
-//    CTA-wide synchronisation.  A CTA covers 32 channels x one pixel chunk; its 4 warps take the
-//    chunk's boxes round-robin.  Shared accumulators are per-warp copies (plain RMW) when K is
-//    small, one CTA-wide copy updated with shared atomics otherwise.
-//  * At the end the CTA adds its [K x 32] partials into the fp64 arena with coalesced RED.F64
-//    (only classes it met): the cross-CTA / cross-image combine is done in fp64.
-//  * `dcfp_class_stats_grouped` runs many resident layers in ONE launch: layer table and tensor
-//    maps travel in kernel parameter space; each CTA binary-searches its layer.
+//  * `dcfp_label_keys` nearest-down-samples the label map in registers ONCE per label resolution into a compact uint8
+//    class-key plane (and counts pixels per class).  Doing it inside the reduction was measured at 27 % of all issued
+//    instructions, repeated by every channel group of every layer.
+//  * channels_last maps -> k1_nhwc.cuh (TMA [G px x 128 ch] boxes, lane = 4 channels, state-free accumulation into a
+//    per-warp slot cache, persistent CTAs);  NCHW maps -> k1_nchw.cuh (TMA [32 ch x 128 B] boxes read back transposed,
+//    lane = channel, per-warp class tables);  tiny / unaligned maps -> the generic kernel below.
+//  * `dcfp_class_stats_grouped` runs many resident layers in ONE launch per path: layer table and tensor maps travel in
+//    kernel parameter space.  CTA partials reach the fp64 arena with RED.F64: the cross-CTA / cross-image combine is fp64.
 #include <math.h>
 
 #include <algorithm>
