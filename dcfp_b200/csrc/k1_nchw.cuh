@@ -1,5 +1,16 @@
-// K1, NCHW feature maps: TMA [32 channels x 128 B] boxes read back transposed (lane = channel).
-// (design notes: class_stats.cu header and DESIGN.md section 4)
+// K1, NCHW feature maps.
+//
+//  * NCHW planes are pixel-contiguous, but the class key varies along pixels and is identical across channels.  Each
+//    warp therefore pulls [32 channels x 128 B] boxes into shared memory with ONE TMA tensor-tile copy
+//    (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier completion) and reads them back TRANSPOSED -- lane == channel --
+//    with conflict-free 128-bit loads.  The class key of every pixel is then warp-uniform.
+//  * Accumulation is state-free (packed FADD2/FFMA2): a box whose 32/64 keys are all equal takes a branch-free path and
+//    one table update; otherwise per quad (4 px, one packed key word), pixel by pixel only in a straddling quad.
+//  * Every warp owns a private 2-stage pipeline (its own mbarriers): no CTA-wide synchronisation in the main loop.  A
+//    CTA covers 32 channels x one pixel chunk (<= 512 KB); its 4 warps take the chunk's boxes round-robin.
+//  * Tables: per-warp [K x 32] float2 copies (plain RMW) for K <= 24; for larger K one CTA-wide copy updated with shared
+//    atomics, fed by a run-length accumulator in registers (RUNLEN) so the table is touched once per class run.
+//  * At the end the CTA adds its partials into the fp64 arena with coalesced RED.F64 (only classes it met).
 #pragma once
 #include <algorithm>
 #include <cstdlib>
