@@ -339,15 +339,32 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     losses = torch.empty(max(len(plan), 1), dtype=torch.float32).pin_memory()
     launches0 = ops.launch_count()
     try:
-        for step, (lo, hi) in enumerate(plan):
+        # host->device copies run one step ahead on their own stream (pinned source, copy engine), so step s+1's
+        # micro-batch is already resident when step s's backward finishes
+        copy_stream = torch.cuda.Stream(device=device)
+        main_stream = torch.cuda.current_stream(device)
+
+        def upload(lo, hi):
             xb, yb = images[lo:hi], labels[lo:hi]
             if not xb.is_pinned():
                 xb, yb = xb.pin_memory(), yb.pin_memory()
-            x = xb.to(device, non_blocking=True)
+            with torch.cuda.stream(copy_stream):
+                x = xb.to(device, non_blocking=True)
+                y = yb.to(device, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            return x, y, ready, xb.numel() * xb.element_size() + yb.numel() * yb.element_size(), (xb, yb)
+
+        nxt = upload(*plan[0]) if plan else None
+        for step, (lo, hi) in enumerate(plan):
+            x, y, ready, nbytes, _pinned = nxt
+            nxt = upload(*plan[step + 1]) if step + 1 < len(plan) else None
+            main_stream.wait_event(ready)
+            x.record_stream(main_stream)  # allocated on the copy stream, consumed on the compute stream
+            y.record_stream(main_stream)
             if nhwc:
                 x = x.contiguous(memory_format=torch.channels_last)
-            y = yb.to(device, non_blocking=True)
-            h2d += xb.numel() * xb.element_size() + yb.numel() * yb.element_size()
+            h2d += nbytes
             loss = run.step(x, y, mb_index=lo // micro_batch)
             losses[step:step + 1].copy_(loss.reshape(1), non_blocking=True)
             d2h += 4
