@@ -339,33 +339,44 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     losses = torch.empty(max(len(plan), 1), dtype=torch.float32).pin_memory()
     launches0 = ops.launch_count()
     try:
-        # host->device copies run one step ahead on their own stream (pinned source, copy engine), so step s+1's
-        # micro-batch is already resident when step s's backward finishes
+        # host->device copies run one step ahead on their own stream into two fixed staging buffers (pinned source,
+        # copy engine): step s+1's micro-batch is already resident when step s's backward finishes.  Fixed buffers,
+        # fenced by events, keep the caching allocator out of it (per-step cross-stream allocations made it re-grow).
         copy_stream = torch.cuda.Stream(device=device)
         main_stream = torch.cuda.current_stream(device)
+        stage = [(torch.empty((micro_batch,) + tuple(images.shape[1:]), dtype=images.dtype, device=device),
+                  torch.empty((micro_batch,) + tuple(labels.shape[1:]), dtype=labels.dtype, device=device)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        pinned = [None, None]
 
-        def upload(lo, hi):
+        def upload(step):
+            lo, hi = plan[step]
+            b = step & 1
             xb, yb = images[lo:hi], labels[lo:hi]
             if not xb.is_pinned():
                 xb, yb = xb.pin_memory(), yb.pin_memory()
+            pinned[b] = (xb, yb)  # keep the pinned source alive until the copy has run
             with torch.cuda.stream(copy_stream):
-                x = xb.to(device, non_blocking=True)
-                y = yb.to(device, non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(copy_stream)
-            return x, y, ready, xb.numel() * xb.element_size() + yb.numel() * yb.element_size(), (xb, yb)
+                if step >= 2:
+                    copy_stream.wait_event(consumed[b])
+                stage[b][0].copy_(xb, non_blocking=True)
+                stage[b][1].copy_(yb, non_blocking=True)
+                ready[b].record(copy_stream)
+            return xb.numel() * xb.element_size() + yb.numel() * yb.element_size()
 
-        nxt = upload(*plan[0]) if plan else None
+        pending_bytes = upload(0) if plan else 0
         for step, (lo, hi) in enumerate(plan):
-            x, y, ready, nbytes, _pinned = nxt
-            nxt = upload(*plan[step + 1]) if step + 1 < len(plan) else None
-            main_stream.wait_event(ready)
-            x.record_stream(main_stream)  # allocated on the copy stream, consumed on the compute stream
-            y.record_stream(main_stream)
+            b = step & 1
+            h2d += pending_bytes
+            if step + 1 < len(plan):
+                pending_bytes = upload(step + 1)
+            main_stream.wait_event(ready[b])
+            x, y = stage[b]
             if nhwc:
                 x = x.contiguous(memory_format=torch.channels_last)
-            h2d += nbytes
             loss = run.step(x, y, mb_index=lo // micro_batch)
+            consumed[b].record(main_stream)
             losses[step:step + 1].copy_(loss.reshape(1), non_blocking=True)
             d2h += 4
         if return_class_stats:
