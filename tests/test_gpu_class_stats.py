@@ -333,3 +333,61 @@ def test_shared_arena_columns_and_guards(native, layout, K):
     mass = ref.abs_mass(x, label, K)
     assert ((S1.cpu() - 2 * r1).abs() <= 2 * RTOL * mass + 1e-30).all()
     assert ((S2.cpu() - 2 * r2).abs() <= 2 * RTOL * r2 + 1e-30).all()
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_maximum_class_count(native, layout):
+    """K = 255 = DCFP_MAX_CLASSES (uint8 keys, 255 is the largest usable class count); label 255 itself is class 254's
+    neighbour 'ignore' only when K < 256 -> with K = 255 every label in [0, 255) is a class and 255 is dropped."""
+    from dcfp_b200 import ops
+    N, C, h, w, K = 2, 128, 32, 32, 255
+    x = torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(255))
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    label = torch.randint(0, 256, (N, h, w), generator=torch.Generator().manual_seed(7), dtype=torch.int64).to(torch.uint8)
+    _check(ops, x, label, K)
+
+
+def test_more_layers_than_one_launch_holds(native):
+    """A grouped call with more layers than one launch's parameter space holds (160 / 128 / 96 / 80 per path) is split
+    transparently; every layer still lands in its own arena columns."""
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    K, n_layers, C = 19, 171, 32
+    g = torch.Generator().manual_seed(5)
+    label = _labels(2, 128, 128, K, torch.uint8, seed=2)
+    keys = ops.label_keys(label.to(dev), 16, 16, K)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        xs = [torch.randn(2, C, 16, 16, generator=g).contiguous(memory_format=fmt) for _ in range(n_layers)]
+        arena = torch.zeros(2, K, n_layers * C, dtype=torch.float64, device=dev)
+        S1 = [arena[0][:, i * C:(i + 1) * C] for i in range(n_layers)]
+        S2 = [arena[1][:, i * C:(i + 1) * C] for i in range(n_layers)]
+        xd = [x.to(dev) for x in xs]
+        ops.class_stats_grouped(xd, [keys] * n_layers, K, S1, S2)
+        dys = [torch.randn_like(x) for x in xd]
+        sc = [torch.ones(C, device=dev)] * n_layers
+        sf = [torch.zeros(C, device=dev)] * n_layers
+        arena_b = torch.zeros_like(arena)
+        ops.class_stats_grouped(xd, [keys] * n_layers, K, [arena_b[0][:, i * C:(i + 1) * C] for i in range(n_layers)],
+                                [arena_b[1][:, i * C:(i + 1) * C] for i in range(n_layers)], dys=dys, scales=sc, shifts=sf)
+        torch.cuda.synchronize()
+        for i in (0, 79, 80, 95, 96, 127, 128, 159, 160, 170):
+            rc, r1, r2 = ref.class_stats(xs[i], label, K)
+            mass = ref.abs_mass(xs[i], label, K)
+            assert ((S1[i].cpu() - r1).abs() <= RTOL * mass + 1e-30).all(), i
+            v = ref.functor_bwd(xs[i], dys[i].cpu(), torch.ones(C), torch.zeros(C))
+            _, b1, _ = ref.class_stats(v, label, K)
+            assert ((arena_b[0][:, i * C:(i + 1) * C].cpu() - b1).abs() <= RTOL * ref.abs_mass(v, label, K) + 1e-30).all(), i
+
+
+def test_empty_and_bad_inputs_are_rejected(native):
+    from dcfp_b200 import ops
+    dev = torch.device("cuda")
+    S = torch.zeros(19, 8, dtype=torch.float64, device=dev)
+    with pytest.raises(RuntimeError, match="bad extent"):
+        ops.class_stats(torch.empty(0, 8, 4, 4, device=dev), torch.empty(0, 4, 4, dtype=torch.uint8, device=dev), 19, S, S.clone())
+    with pytest.raises(RuntimeError, match="fp32 or bf16"):
+        ops.class_stats(torch.zeros(1, 8, 4, 4, device=dev, dtype=torch.float16), torch.zeros(1, 4, 4, dtype=torch.uint8, device=dev),
+                        19, S, S.clone())
+    with pytest.raises(RuntimeError, match="empty layer list"):
+        ops.class_stats_grouped([], [], 19, [], [])
