@@ -8,8 +8,8 @@
 //    one table update; otherwise per quad (4 px, one packed key word), pixel by pixel only in a straddling quad.
 //  * Every warp owns a private 2-stage pipeline (its own mbarriers): no CTA-wide synchronisation in the main loop.  A
 //    CTA covers 32 channels x one pixel chunk (<= 512 KB); its 4 warps take the chunk's boxes round-robin.
-//  * Tables: per-warp [K x 32] float2 copies (plain RMW) for K <= 24; for larger K one CTA-wide copy updated with shared
-//    atomics, fed by a run-length accumulator in registers (RUNLEN) so the table is touched once per class run.
+//  * Tables: per-warp [K x 32] float2 copies (plain RMW) for K <= 24; for larger K the CTA scans its tile's keys once,
+//    builds a class -> row remap (rank among the classes present) and every warp keeps a private 32-row table.
 //  * At the end the CTA adds its partials into the fp64 arena with coalesced RED.F64 (only classes it met).
 #pragma once
 #include <algorithm>
@@ -21,7 +21,7 @@ namespace dcfp {
 namespace {
 
 constexpr int kWarpsPrivate = 4;  // warps per CTA when every warp owns an accumulator table (small K)
-constexpr int kWarpsShared = 8;   // warps per CTA sharing one table through shared atomics (large K)
+constexpr int kRemapRows = 32;     // table rows per warp in the large-K mode (classes met by one tile)
 constexpr int kBoxRowBytes = 128;                 // SWIZZLE_128B span
 constexpr int kBoxBytes = 32 * kBoxRowBytes;      // one [32 channels x 128 B] box = 4 KB
 constexpr int kGroups = kBoxRowBytes / 16;        // 128-bit groups per row (8)
@@ -56,19 +56,12 @@ constexpr int kBigGroupBwd = 96;   //  96 * (256 + 64) B  = 30.0 KB
 // acc[key][lane] += (a1, a2): the shared accumulator is an interleaved float2 [K][32] table, so one
 // 64-bit load / FADD2 / 64-bit store updates both moments of (class, channel).  Lanes touch
 // consecutive 8-byte slots: conflict-free.
-template <bool SHARED_ACC>
-__device__ __forceinline__ void acc_add(uint32_t acc_lane, unsigned key, float a1, float a2) {
-  const uint32_t addr = acc_lane + key * 256u;
-  if (SHARED_ACC) {  // one CTA-wide table (large K): shared-memory atomics
-    float* p = reinterpret_cast<float*>(__cvta_shared_to_generic(addr));
-    atomicAdd(p, a1);
-    atomicAdd(p + 1, a2);
-  } else {  // per-warp table: plain read-modify-write
-    f2 cur;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cur) : "r"(addr));
-    cur = add2(cur, pack2(a1, a2));
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(cur) : "memory");
-  }
+__device__ __forceinline__ void acc_add_row(uint32_t acc_lane, unsigned row, float a1, float a2) {
+  const uint32_t addr = acc_lane + row * 256u;  // per-warp table: plain read-modify-write
+  f2 cur;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cur) : "r"(addr));
+  cur = add2(cur, pack2(a1, a2));
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(cur) : "memory");
 }
 
 // value of one pixel re-read from the staged box (per-pixel path of a quad that straddles a class
@@ -116,9 +109,13 @@ struct BoxCursor {
   }
 };
 
-// RUNLEN: keep the current class run (key, sum, sum of squares) in registers and touch the shared table only
-// when the class changes -- the table of the large-K variant is updated with shared atomics (2 x ~64 cycles
-// per warp-wide update), so the number of updates, not of pixels, is what it can afford.
+// SHARED_ACC (historic name; K > 24): a table with one row per class does not fit per warp (K x 256 B), but a TILE only
+// meets a few classes (labels are spatially coherent).  The CTA first scans the tile's class keys into a presence
+// bitmap and builds a class -> row REMAP in shared memory (rank of the class among those present); every warp then
+// keeps a private 32-row table addressed through it.  Classes beyond the 32nd present one (rare) go straight to the
+// arena.  (Earlier large-K variants: one CTA-wide [K x 32] table behind shared atomics, 43-57 % of the roofline -- 2 x
+// ~64 LSU cycles per update; a per-warp slot cache with ballot lookups, 44-54 % -- per-quad lookup cost.)
+// RUNLEN (unused) keeps a class run in registers.
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, bool RUNLEN>
 __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMap* maps, const int K, const int stages,
                                              const int tile, unsigned char* smem) {
@@ -126,7 +123,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   constexpr int kWords = kBoxPx / 4;                                  // packed key words (quads) per box
   constexpr int kQuadsPerGroup = kWords / kGroups;                    // 1 (fp32) / 2 (bf16)
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int kAccCopies = SHARED_ACC ? 1 : WARPS;
+  constexpr int kAccCopies = WARPS;
   constexpr int kPairs = Elem<T>::kPairs;
   constexpr int kStageBytes = kTens * kBoxBytes;
   constexpr int kThreadsT = WARPS * 32;
@@ -138,9 +135,16 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   // ---- shared-memory carve-up: [boxes | accumulators (float2 [copies][K][32]) | mbarriers] -------
   unsigned char* bufs = smem;  // [WARPS][stages][kTens][kBoxBytes], 1024-B aligned
   float2* acc = reinterpret_cast<float2*>(smem + static_cast<size_t>(WARPS) * stages * kStageBytes);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(acc + kAccCopies * K * 32);
+  const int rows = SHARED_ACC ? kRemapRows : K;  // table rows per warp
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(acc + kAccCopies * rows * 32);
+  // large-K mode: class -> row remap of this tile, its inverse, the presence bitmap
+  unsigned char* remap = reinterpret_cast<unsigned char*>(bars + WARPS * stages);  // [256]
+  unsigned char* row_class = remap + 256;                                          // [kRemapRows]
+  unsigned* present = reinterpret_cast<unsigned*>(row_class + kRemapRows);         // [8]
+  constexpr unsigned kOverflow = 0xfeu;
 
-  for (int i = tid; i < kAccCopies * K * 32; i += kThreadsT) acc[i] = make_float2(0.f, 0.f);
+  for (int i = tid; i < kAccCopies * rows * 32; i += kThreadsT) acc[i] = make_float2(0.f, 0.f);
+  if (SHARED_ACC && tid < 8) present[tid] = 0u;
   if (tid < WARPS * stages) mbar_init(smem_u32(&bars[tid]), 1);
   mbar_fence_init();
   __syncthreads();
@@ -151,8 +155,64 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   const uint64_t policy = policy_evict_first();
   const uint32_t my_bufs = smem_u32(bufs + static_cast<size_t>(warp) * stages * kStageBytes);
   const uint32_t my_bars = smem_u32(&bars[warp * stages]);
-  const uint32_t acc_lane = smem_u32(acc + (SHARED_ACC ? 0 : warp * K * 32) + lane);
+  const uint32_t acc_lane = smem_u32(acc + warp * rows * 32 + lane);
   const int row0 = cg * 32;
+
+  int n_rows = 0;
+  if (SHARED_ACC) {
+    // (1) presence bitmap of the tile's keys (consecutive duplicates skipped), (2) rank -> remap
+    const int n_words = (box_end - box_begin) * kWords;
+    unsigned prev = 0xffffffffu;
+    for (int wi = tid; wi < n_words; wi += kThreadsT) {
+      const int box = box_begin + wi / kWords, word = wi % kWords;
+      const int n = box / L.boxes_per_plane, b = box - n * L.boxes_per_plane;
+      const int p = b * kBoxPx + 4 * word;
+      if (p >= L.HW) continue;
+      const unsigned w = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(n) * L.HW + p)) : 0u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned k = (w >> (8 * e)) & 0xffu;
+        if (k != prev && k < static_cast<unsigned>(K)) atomicOr(&present[k >> 5], 1u << (k & 31));
+        prev = k;
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < 256; k += kThreadsT) {
+      const unsigned word = present[k >> 5], bit = 1u << (k & 31);
+      unsigned char r = 0xffu;
+      if (word & bit) {
+        int rank = __popc(word & (bit - 1u));
+        for (int j = 0; j < (k >> 5); ++j) rank += __popc(present[j]);
+        r = rank < kRemapRows ? static_cast<unsigned char>(rank) : static_cast<unsigned char>(kOverflow);
+        if (rank < kRemapRows) row_class[rank] = static_cast<unsigned char>(k);
+      }
+      remap[k] = r;
+    }
+    int total = 0;
+    for (int j = 0; j < 8; ++j) total += __popc(present[j]);
+    n_rows = min(total, kRemapRows);
+    __syncthreads();
+  }
+  unsigned last_key = 0xffffffffu, last_row = 0;
+  auto acc_add = [&](unsigned key, float a1, float a2) {
+    if (!SHARED_ACC) {
+      acc_add_row(acc_lane, key, a1, a2);
+      return;
+    }
+    if (key != last_key) {
+      last_key = key;
+      last_row = remap[key];
+    }
+    if (last_row == kOverflow) {  // more than 32 classes in this tile: the rest goes straight to the arena
+      if (lane < n_active) {
+        const size_t o = static_cast<size_t>(key) * L.ld + row0 + lane;
+        atomicAdd(&L.S1[o], static_cast<double>(a1));
+        atomicAdd(&L.S2[o], static_cast<double>(a2));
+      }
+      return;
+    }
+    acc_add_row(acc_lane, last_row, a1, a2);
+  };
 
   BoxCursor issue_at, key_at;
   issue_at.n = (box_begin + warp) / L.boxes_per_plane;
@@ -209,7 +269,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   float run1 = 0.f, run2 = 0.f;
   auto run_add = [&](unsigned key, float a1, float a2) {  // key is warp-uniform: no divergence
     if (key != run_key) {
-      if (run_key < static_cast<unsigned>(K)) acc_add<SHARED_ACC>(acc_lane, run_key, run1, run2);
+      if (run_key < static_cast<unsigned>(K)) acc_add(run_key, run1, run2);
       run_key = key;
       run1 = a1;
       run2 = a2;
@@ -247,7 +307,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
         s1a = add2(s1a, s1b);
         s2a = add2(s2a, s2b);
         if (RUNLEN) run_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
-        else acc_add<SHARED_ACC>(acc_lane, key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
+        else acc_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
       } else if (RUNLEN) {
         run_add(static_cast<unsigned>(K), 0.f, 0.f);  // dropped pixels close the open run
       }
@@ -268,7 +328,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
               const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
               const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
               if (RUNLEN) run_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
-              else acc_add<SHARED_ACC>(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+              else acc_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
             } else if (RUNLEN) {
               run_add(static_cast<unsigned>(K), 0.f, 0.f);
             }
@@ -279,7 +339,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
               if (ke < static_cast<unsigned>(K)) {
                 const float x = load_px<T, BWD, AFFINE>(gaddr + (h * 4 + e) * static_cast<int>(sizeof(T)), sc, sf);
                 if (RUNLEN) run_add(ke, x, x * x);
-                else acc_add<SHARED_ACC>(acc_lane, ke, x, x * x);
+                else acc_add(ke, x, x * x);
               } else if (RUNLEN) {
                 run_add(static_cast<unsigned>(K), 0.f, 0.f);
               }
@@ -300,17 +360,19 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   __syncthreads();
 
   // ---- CTA partials -> fp64 arena (coalesced RED.F64; zero partials are skipped) ----------------
-  for (int idx = tid; idx < K * 32; idx += kThreadsT) {
-    const int k = idx >> 5, cl = idx & 31;
+  const int used_rows = SHARED_ACC ? n_rows : K;
+  for (int idx = tid; idx < used_rows * 32; idx += kThreadsT) {
+    const int r = idx >> 5, cl = idx & 31;
     if (cl >= n_active) continue;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int w = 0; w < kAccCopies; ++w) {
-      const float2 a = acc[w * K * 32 + idx];
+      const float2 a = acc[w * rows * 32 + idx];
       s1 += a.x;
       s2 += a.y;
     }
     if (s1 == 0.f && s2 == 0.f) continue;  // class not met by this CTA (or all-zero values): nothing to add
+    const int k = SHARED_ACC ? row_class[r] : r;
     const size_t o = static_cast<size_t>(k) * L.ld + row0 + cl;
     atomicAdd(&L.S1[o], static_cast<double>(s1));
     atomicAdd(&L.S2[o], static_cast<double>(s2));
@@ -318,7 +380,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
 }
 
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL, bool RUNLEN>
-__global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 2 : 4)
+__global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 3 : 4)
     class_stats_kernel(const __grid_constant__ GroupParams<MAXL, BWD ? 2 : 1> P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned; SWIZZLE_128B boxes need 1024 B
@@ -352,10 +414,10 @@ int make_map(CUtensorMap* map, const void* base, int dtype, long long rows, long
 }
 
 size_t tile_smem_bytes(int K, bool bwd, bool shared_acc, int stages) {
-  const int warps = shared_acc ? kWarpsShared : kWarpsPrivate;
-  const int copies = shared_acc ? 1 : warps;
-  return static_cast<size_t>(warps) * stages * (bwd ? 2 : 1) * kBoxBytes + static_cast<size_t>(copies) * K * 32 * 8 +
-         8 * warps * stages + 1024 /* base alignment slack */;
+  const int warps = kWarpsPrivate;
+  const int rows = shared_acc ? kRemapRows : K;  // tile-local remap vs one row per class
+  return static_cast<size_t>(warps) * stages * (bwd ? 2 : 1) * kBoxBytes + static_cast<size_t>(warps) * rows * 32 * 8 +
+         8 * warps * stages + (shared_acc ? 256 + kRemapRows + 32 : 0) + 1024 /* base alignment slack */;
 }
 
 // the TMA path needs 16-B aligned planes and word-aligned key rows; everything else is generic
@@ -381,10 +443,10 @@ int pick_stages() {
 
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int MAXL>
 int launch_tiled(GroupParams<MAXL, BWD ? 2 : 1>& P, int n_tiles, cudaStream_t stream) {
-  constexpr int kWarpsT = SHARED_ACC ? kWarpsShared : kWarpsPrivate;
+  constexpr int kWarpsT = kWarpsPrivate;
   P.stages = pick_stages();
   const size_t smem = tile_smem_bytes(P.K, BWD, SHARED_ACC, P.stages);
-  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL, SHARED_ACC>;
+  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL, false>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
   kern<<<n_tiles, kWarpsT * 32, smem, stream>>>(P);
@@ -427,7 +489,7 @@ int run_tiled(const dcfp_layer_desc* descs, const int* which, int n, int boxes_p
   }
   const int n_tiles = P.tile_prefix[n];
   if (n_tiles == 0) return 0;
-  if (K > kPrivateAccMaxK) {  // one CTA-wide accumulator copy, shared atomics; [K x 32 x 2] floats
+  if (K > kPrivateAccMaxK) {  // tile-local class remap, 32 table rows per warp
     if (BWD || affine) return launch_tiled<T, BWD, true, true, MAXL>(P, n_tiles, stream);
     return launch_tiled<T, BWD, false, true, MAXL>(P, n_tiles, stream);
   }

@@ -391,3 +391,17 @@ def test_empty_and_bad_inputs_are_rejected(native):
                         19, S, S.clone())
     with pytest.raises(RuntimeError, match="empty layer list"):
         ops.class_stats_grouped([], [], 19, [], [])
+
+
+@pytest.mark.parametrize("K", [40, 171, 255])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_nchw_large_k_remap_overflow(native, K, dtype):
+    """NCHW, K > 24: i.i.d. labels put far more than 32 classes into every tile -> the classes beyond the 32 remapped
+    rows take the direct-to-arena path."""
+    from dcfp_b200 import ops
+    N, C, h, w = 2, 64, 32, 64
+    x = (torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(K)) * 1.3).to(dtype)
+    label = torch.randint(0, K, (N, h, w), generator=torch.Generator().manual_seed(K + 1)).to(torch.uint8)
+    _check(ops, x, label, K)
+    dy = (torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(K + 2)) * 1e-2).to(dtype)
+    _check(ops, x, label, K, dy=dy, scale=torch.rand(C) + 0.5, shift=torch.randn(C))
