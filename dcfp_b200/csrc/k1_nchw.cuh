@@ -9,7 +9,7 @@
 //  * Every warp owns a private 2-stage pipeline (its own mbarriers): no CTA-wide synchronisation in the main loop.  A
 //    CTA covers 32 channels x one pixel chunk (<= 512 KB); its 4 warps take the chunk's boxes round-robin.
 //  * Tables: per-warp [K x 32] float2 copies (plain RMW) for K <= 24; for larger K the CTA scans its tile's keys once,
-//    builds a class -> row remap (rank among the classes present) and every warp keeps a private 32-row table.
+//    builds a class -> row remap (rank among the classes present) and every warp keeps a private 24-row table.
 //  * At the end the CTA adds its partials into the fp64 arena with coalesced RED.F64 (only classes it met).
 #pragma once
 #include <algorithm>
@@ -21,7 +21,7 @@ namespace dcfp {
 namespace {
 
 constexpr int kWarpsPrivate = 4;  // warps per CTA when every warp owns an accumulator table (small K)
-constexpr int kRemapRows = 32;     // table rows per warp in the large-K mode (classes met by one tile)
+constexpr int kRemapRows = 24;     // table rows per warp in the large-K mode (classes met by one tile)
 constexpr int kBoxRowBytes = 128;                 // SWIZZLE_128B span
 constexpr int kBoxBytes = 32 * kBoxRowBytes;      // one [32 channels x 128 B] box = 4 KB
 constexpr int kGroups = kBoxRowBytes / 16;        // 128-bit groups per row (8)
@@ -112,7 +112,7 @@ struct BoxCursor {
 // SHARED_ACC (historic name; K > 24): a table with one row per class does not fit per warp (K x 256 B), but a TILE only
 // meets a few classes (labels are spatially coherent).  The CTA first scans the tile's class keys into a presence
 // bitmap and builds a class -> row REMAP in shared memory (rank of the class among those present); every warp then
-// keeps a private 32-row table addressed through it.  Classes beyond the 32nd present one (rare) go straight to the
+// keeps a private 24-row table addressed through it.  Classes beyond the 24th present one (rare) go straight to the
 // arena.  (Earlier large-K variants: one CTA-wide [K x 32] table behind shared atomics, 43-57 % of the roofline -- 2 x
 // ~64 LSU cycles per update; a per-warp slot cache with ballot lookups, 44-54 % -- per-quad lookup cost.)
 // RUNLEN (unused) keeps a class run in registers.
@@ -159,40 +159,6 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   const int row0 = cg * 32;
 
   int n_rows = 0;
-  if (SHARED_ACC) {
-    // (1) presence bitmap of the tile's keys (consecutive duplicates skipped), (2) rank -> remap
-    const int n_words = (box_end - box_begin) * kWords;
-    unsigned prev = 0xffffffffu;
-    for (int wi = tid; wi < n_words; wi += kThreadsT) {
-      const int box = box_begin + wi / kWords, word = wi % kWords;
-      const int n = box / L.boxes_per_plane, b = box - n * L.boxes_per_plane;
-      const int p = b * kBoxPx + 4 * word;
-      if (p >= L.HW) continue;
-      const unsigned w = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(n) * L.HW + p)) : 0u;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned k = (w >> (8 * e)) & 0xffu;
-        if (k != prev && k < static_cast<unsigned>(K)) atomicOr(&present[k >> 5], 1u << (k & 31));
-        prev = k;
-      }
-    }
-    __syncthreads();
-    for (int k = tid; k < 256; k += kThreadsT) {
-      const unsigned word = present[k >> 5], bit = 1u << (k & 31);
-      unsigned char r = 0xffu;
-      if (word & bit) {
-        int rank = __popc(word & (bit - 1u));
-        for (int j = 0; j < (k >> 5); ++j) rank += __popc(present[j]);
-        r = rank < kRemapRows ? static_cast<unsigned char>(rank) : static_cast<unsigned char>(kOverflow);
-        if (rank < kRemapRows) row_class[rank] = static_cast<unsigned char>(k);
-      }
-      remap[k] = r;
-    }
-    int total = 0;
-    for (int j = 0; j < 8; ++j) total += __popc(present[j]);
-    n_rows = min(total, kRemapRows);
-    __syncthreads();
-  }
   unsigned last_key = 0xffffffffu, last_row = 0;
   auto acc_add = [&](unsigned key, float a1, float a2) {
     if (!SHARED_ACC) {
@@ -258,6 +224,52 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   const f2 sc2 = pack2(sc, sc), sf2 = pack2(sf, sf);
 
   for (int s = 0; s < stages; ++s) issue();
+  // the first boxes are already in flight while the CTA scans its tile's class keys
+  if (SHARED_ACC) {
+    // (1) presence bitmap of the tile's keys (consecutive duplicates skipped), (2) rank -> remap
+    const int n_words = (box_end - box_begin) * kWords;
+    const unsigned none = static_cast<unsigned>(K) * 0x01010101u;
+    unsigned prev = 0xffffffffu;
+    for (int base = 0; base < n_words; base += kThreadsT * 8) {
+      unsigned w[8];  // 8 independent loads in flight per thread: the scan costs ~one L2 latency per tile
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int wi = base + j * kThreadsT + tid;
+        w[j] = none;
+        if (wi < n_words) {
+          const int box = box_begin + wi / kWords, word = wi % kWords;
+          const int n = box / L.boxes_per_plane, b = box - n * L.boxes_per_plane;
+          const int p = b * kBoxPx + 4 * word;
+          if (p < L.HW) w[j] = L.keys ? __ldg(reinterpret_cast<const unsigned*>(L.keys + static_cast<size_t>(n) * L.HW + p)) : 0u;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned k = (w[j] >> (8 * e)) & 0xffu;
+          if (k != prev && k < static_cast<unsigned>(K)) atomicOr(&present[k >> 5], 1u << (k & 31));
+          prev = k;
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < 256; k += kThreadsT) {
+      const unsigned word = present[k >> 5], bit = 1u << (k & 31);
+      unsigned char r = 0xffu;
+      if (word & bit) {
+        int rank = __popc(word & (bit - 1u));
+        for (int j = 0; j < (k >> 5); ++j) rank += __popc(present[j]);
+        r = rank < kRemapRows ? static_cast<unsigned char>(rank) : static_cast<unsigned char>(kOverflow);
+        if (rank < kRemapRows) row_class[rank] = static_cast<unsigned char>(k);
+      }
+      remap[k] = r;
+    }
+    int total = 0;
+    for (int j = 0; j < 8; ++j) total += __popc(present[j]);
+    n_rows = min(total, kRemapRows);
+    __syncthreads();
+  }
   unsigned lw = key_word();
 
   // SWIZZLE_128B: the 16-B chunk index of row r is XORed with r % 8 (lane == row)
@@ -313,7 +325,16 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
       }
     } else {
       // a class boundary crosses the box: per quad (4 px, one packed key word) -- a quad with one
-      // class is summed in registers and added to the table; a straddling quad goes pixel by pixel
+      // class is summed in registers and added to the table; a straddling quad goes pixel by pixel.
+      // Large-K mode: every lane first translates ITS key word to table rows through the tile's remap (4 byte
+      // look-ups per lane per box instead of one look-up per quad in the loop below).
+      unsigned rw = lw;
+      if (SHARED_ACC && !RUNLEN) {
+        rw = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rw |= static_cast<unsigned>(remap[(lw >> (8 * e)) & 0xffu]) << (8 * e);
+      }
+      const unsigned row_limit = SHARED_ACC ? static_cast<unsigned>(kRemapRows) : static_cast<unsigned>(K);
 #pragma unroll 1
       for (int g = 0; g < kGroups; ++g) {
         const uint32_t gaddr = box + ((static_cast<uint32_t>(g) ^ l7) << 4);
@@ -321,21 +342,27 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
         load_group<T, BWD, AFFINE>(gaddr, sc2, sf2, v);
 #pragma unroll
         for (int h = 0; h < kQuadsPerGroup; ++h) {
-          const unsigned wv = __shfl_sync(0xffffffffu, lw, g * kQuadsPerGroup + h);
-          const unsigned key = wv & 0xffu;
-          if (wv == key * 0x01010101u) {
-            if (key < static_cast<unsigned>(K)) {
+          const unsigned wv = __shfl_sync(0xffffffffu, RUNLEN ? lw : rw, g * kQuadsPerGroup + h);
+          const unsigned key = wv & 0xffu;  // a table row (or, with RUNLEN, a class)
+          if (wv == key * 0x01010101u && (RUNLEN || !SHARED_ACC || key != kOverflow)) {
+            if (RUNLEN) {
+              if (key < static_cast<unsigned>(K)) {
+                const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
+                const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
+                run_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
+              } else {
+                run_add(static_cast<unsigned>(K), 0.f, 0.f);
+              }
+            } else if (key < row_limit) {
               const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
               const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
-              if (RUNLEN) run_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
-              else acc_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
-            } else if (RUNLEN) {
-              run_add(static_cast<unsigned>(K), 0.f, 0.f);
+              acc_add_row(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
             }
-          } else {
+          } else {  // straddling quad, or (large-K mode) a quad of overflow classes: pixel by pixel, by class
+            const unsigned kv = SHARED_ACC && !RUNLEN ? __shfl_sync(0xffffffffu, lw, g * kQuadsPerGroup + h) : wv;
 #pragma unroll 1
             for (int e = 0; e < 4; ++e) {
-              const unsigned ke = (wv >> (8 * e)) & 0xffu;
+              const unsigned ke = (kv >> (8 * e)) & 0xffu;
               if (ke < static_cast<unsigned>(K)) {
                 const float x = load_px<T, BWD, AFFINE>(gaddr + (h * 4 + e) * static_cast<int>(sizeof(T)), sc, sf);
                 if (RUNLEN) run_add(ke, x, x * x);
@@ -380,7 +407,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
 }
 
 template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL, bool RUNLEN>
-__global__ void __launch_bounds__(WARPS * 32, SHARED_ACC ? 3 : 4)
+__global__ void __launch_bounds__(WARPS * 32, 4)
     class_stats_kernel(const __grid_constant__ GroupParams<MAXL, BWD ? 2 : 1> P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned; SWIZZLE_128B boxes need 1024 B
