@@ -59,6 +59,9 @@ def parse_args():
     p.add_argument("--layout", default="channels_last", choices=["channels_last", "nchw"],
                    help="memory format of the model / feature maps: channels_last is cuDNN's native tensor-core layout "
                         "(no per-conv transposes) and takes K1's NHWC path; nchw takes K1's TMA-tile path")
+    p.add_argument("--scores-only", action="store_true",
+                   help="freeze every non-BN parameter during scoring: no weight-gradient convolutions (the scores do not "
+                        "need them); default off = the reference's full backward")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock cap of the reference arm")
@@ -258,7 +261,8 @@ def run_b200_arm(args, c):
         return float(t.item())
 
     # ---- phase A: inputs resident in HBM -------------------------------------------------------------------
-    run = CalibrationRun(model, c["num_classes"], r=0.999, flush_bytes=args.flush_mb << 20, keep_totals=True, timing=True, seed=0)
+    run = CalibrationRun(model, c["num_classes"], r=0.999, flush_bytes=args.flush_mb << 20, keep_totals=True, timing=True, seed=0,
+                         scores_only=args.scores_only)
     sc = run.scorer
     # nvidia-smi attaches to the driver when it starts (stalls launches for ~0.2 s): start it before the set-up steps
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
@@ -341,12 +345,14 @@ def run_b200_arm(args, c):
             return torch.cat(xs).pin_memory(), torch.cat(ys).pin_memory()
         if W:
             xw, yw = global_order(0, W)
-            score_calibration_set(model, xw, yw, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20)
+            score_calibration_set(model, xw, yw, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20,
+                                  scores_only=args.scores_only)
         xk, yk = global_order(W, W + K)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = score_calibration_set(model, xk, yk, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20)
+        out = score_calibration_set(model, xk, yk, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20,
+                                    scores_only=args.scores_only)
         e1.record()
         barrier()
         ms_b = max_over_ranks(e0.elapsed_time(e1))
@@ -371,7 +377,8 @@ def run_b200_arm(args, c):
                 "traffic_note": traffic.get("note") if traffic else "no ncu --set full capture recorded yet",
                 "launches": k1_launches, "algorithmic_bytes_per_launch": k1_bytes / max(k1_launches, 1),
                 "avg_launch_ms": k1_ms / max(k1_launches, 1), "share_of_step": share_a,
-                "algorithmic_bytes_per_image": k1_bytes / (K * mb)}
+                "algorithmic_bytes_per_image": k1_bytes / (K * mb),
+                "images_per_s_of_kernel_time": K * mb / (k1_ms * 1e-3) if k1_ms > 0 else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,7 +396,7 @@ def run_b200_arm(args, c):
                            "protocol": "zero_grad -> loss(x, y, deepsup) -> backward [K1 on every scored BN: S[k,c] += dy*xhat] -> "
                                        "fold -> all-reduce(dgamma)/N -> EIC update; no optimizer step",
                            "l2": "per-step feature maps (%.1f GB read by K1) exceed the 126 MB L2; no explicit flush" % (k1_bytes / K / 1e9),
-                           "layout": args.layout, "k1_flush_mib": args.flush_mb, "priming_steps": args.prime, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
+                           "layout": args.layout, "backward": "scores_only (no weight-gradient convolutions)" if args.scores_only else "full (all gradients, as the reference's training step)", "k1_flush_mib": args.flush_mb, "priming_steps": args.prime, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
                 "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K,sumC] fp64 totals + counts at the end of the pass"}}
         print(json.dumps(line), flush=True)

@@ -267,10 +267,21 @@ class CalibrationRun:
     all-reduce before the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
 
     def __init__(self, model, num_classes, r=0.999, mode="bwd", restore_bn_stats=True, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, process_group=None, seed=None):
+                 timing=False, process_group=None, seed=None, scores_only=False):
         ops.require_gpu()
         self.model = model
         self.seed = seed
+        # scores_only: the EIC needs d(loss)/d(gamma) of the BN layers only, and K1 computes it from (x, dy) itself.
+        # Freezing every non-BN parameter keeps the activation-gradient chain (dgrad) but drops the weight-gradient
+        # convolutions (wgrad, ~17 % of a c2 step) that the reference's training loop needs for its optimizer and a
+        # calibration pass does not.  Off by default: the default step does the reference's full backward.
+        self._frozen = []
+        if scores_only:
+            bn_params = {id(p) for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) for p in m.parameters()}
+            for p_ in model.parameters():
+                if id(p_) not in bn_params and p_.requires_grad:
+                    p_.requires_grad_(False)
+                    self._frozen.append(p_)
         self.device = next(model.parameters()).device
         self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
                                        keep_totals=keep_totals, timing=timing).attach()
@@ -306,6 +317,9 @@ class CalibrationRun:
         if self.closed:
             return
         self.closed = True
+        for p_ in self._frozen:
+            p_.requires_grad_(True)
+        self._frozen = []
         self.scorer.detach()
         self.model.train(self._was_training)
         self.model.zero_grad(set_to_none=True)
@@ -318,7 +332,7 @@ class CalibrationRun:
 
 
 def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, flush_bytes=1 << 30,
-                          return_class_stats=False, seed=0):
+                          return_class_stats=False, seed=0, scores_only=False):
     """Public end-to-end call: HOST images [n,3,H,W] / labels [n,H,W] -> EIC scores on the host.
 
     Every step copies its micro-batch host->device from pinned memory and reads the step's loss back;
@@ -334,7 +348,7 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     rank = torch.distributed.get_rank() if dist_on else 0
     plan = shard_plan(images.shape[0], micro_batch, world, rank)
     run = CalibrationRun(model, num_classes, r=r, restore_bn_stats=restore_bn_stats, flush_bytes=flush_bytes,
-                         keep_totals=return_class_stats, seed=seed)
+                         keep_totals=return_class_stats, seed=seed, scores_only=scores_only)
     h2d = d2h = 0
     losses = torch.empty(max(len(plan), 1), dtype=torch.float32).pin_memory()
     launches0 = ops.launch_count()

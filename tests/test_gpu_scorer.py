@@ -200,3 +200,18 @@ def test_steady_state_memory_and_channels_last_model(native, channels_last):
     ok = _close(S1, g)
     assert ok.mean() > 0.999, "%d channels off" % (~ok).sum()
     run.close()
+
+
+def test_scores_only_mode_gives_the_same_scores(native):
+    """Freezing the non-BN parameters (no weight-gradient convolutions) changes nothing the score depends on."""
+    from dcfp_b200.scorer import score_calibration_set
+    model = _setup()
+    x, y = _batch(list(range(4)))
+    a = score_calibration_set(model, x, y, K, seed=2)
+    b = score_calibration_set(model, x, y, K, seed=2, scores_only=True)
+    assert all(p.requires_grad for p in model.parameters())
+    va = np.concatenate([v.numpy() for v in a["eic"].values()])
+    vb = np.concatenate([v.numpy() for v in b["eic"].values()])
+    close = np.abs(va - vb) <= 2e-2 * np.abs(va) + 2e-2 * np.abs(va).mean()
+    assert close.mean() > 0.99
+    assert all(m.weight.grad is None for m in model.modules() if isinstance(m, torch.nn.Conv2d))
