@@ -33,9 +33,9 @@ namespace {
 constexpr int kNhwcWarps = 8;
 constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
 constexpr int kNhwcSlots = 12;       // class rows per warp (tag of row i lives in lane i)
-// one staged box = [G px][128 ch]: 8 KB forward (G = 16 fp32 / 32 bf16), 4 KB per tensor backward (x and dy boxes):
+// one staged box = [G px][128 ch]: 8 KB fp32 forward (G = 16), 4 KB bf16 forward (G = 16), 4 KB per tensor backward:
 // 8 KB per pipeline stage either way, so the fixed per-iteration work (wait, key broadcast, refill) is paid per 8 KB
-__host__ __device__ constexpr int nhwc_box_bytes(bool bwd) { return bwd ? 4096 : 8192; }
+__host__ __device__ constexpr int nhwc_box_bytes(bool bwd, int elem_size = 4) { return (bwd || elem_size == 2) ? 4096 : 8192; }
 
 struct NhwcLayer {
   const uint8_t* keys;  // [N*HW]
@@ -91,7 +91,7 @@ constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-bo
 template <typename T, bool BWD, bool AFFINE, int MAXL>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P) {
-  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD);
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)));
   constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
   constexpr int kTens = BWD ? 2 : 1;
@@ -469,7 +469,7 @@ bool nhwc_ok(const dcfp_layer_desc& d) {
 template <typename T, bool BWD, int MAXL>
 int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long target_bytes, cudaStream_t stream) {
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD);
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)));
   constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   const int K = descs[which[0]].K;
   NhwcParams<MAXL, kTens> P;
