@@ -29,11 +29,30 @@ def _nvcc():
     return exe if os.path.exists(exe) else (shutil.which("nvcc") or "nvcc")
 
 
-def _stale(target, sources):
-    if not os.path.exists(target):
+def _digest(sources, extra=""):
+    """Content hash of the inputs of a build step (file names + bytes + flags)."""
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, sources, extra=""):
+    """Rebuild when the target is missing or was built from different inputs.  Content hashes, not mtimes: the repo
+    travels to the GPU box as a snapshot whose timestamps say nothing about what the shipped .so was built from."""
+    stamp = target + ".stamp"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    with open(stamp) as f:
+        return f.read().strip() != _digest(sources, extra)
+
+
+def _write_stamp(target, sources, extra=""):
+    with open(target + ".stamp", "w") as f:
+        f.write(_digest(sources, extra))
 
 
 def _run(cmd, verbose):
@@ -50,7 +69,8 @@ def build_abi(force=False, verbose=False, ptxas_verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in CU_SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(INCLUDE, "dcfp_b200.h")]
-    if not force and not _stale(ABI_LIB, deps):
+    flags = " ".join(NVCC_FLAGS)
+    if not force and not _stale(ABI_LIB, deps, flags):
         return ABI_LIB
     objs = []
     procs = []
@@ -70,6 +90,7 @@ def build_abi(force=False, verbose=False, ptxas_verbose=False):
     _run([_nvcc(), "-shared", "-cudart", "static", "-o", ABI_LIB] + objs, verbose)
     for o in objs:
         os.remove(o)
+    _write_stamp(ABI_LIB, deps, flags)
     return ABI_LIB
 
 
@@ -78,8 +99,9 @@ def build_torch_ops(force=False, verbose=False):
     from torch.utils import cpp_extension as ce
 
     src = os.path.join(CSRC, "torch_binding.cpp")
-    deps = [src, os.path.join(INCLUDE, "dcfp_b200.h"), ABI_LIB]
-    if not force and not _stale(OPS_LIB, deps):
+    deps = [src, os.path.join(INCLUDE, "dcfp_b200.h")]
+    extra = "torch " + torch.__version__ + " abi " + (open(ABI_LIB + ".stamp").read() if os.path.exists(ABI_LIB + ".stamp") else "")
+    if not force and not _stale(OPS_LIB, deps, extra):
         return OPS_LIB
     cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     inc = []
@@ -90,6 +112,7 @@ def build_torch_ops(force=False, verbose=False):
             "-DTORCH_API_INCLUDE_EXTENSION_H", "-w"] + inc + [src, "-o", OPS_LIB, "-L", LIBDIR, "-ldcfp_b200", "-L", torch_lib,
             "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + torch_lib])
     _run(cmd, verbose)
+    _write_stamp(OPS_LIB, deps, extra)
     return OPS_LIB
 
 
