@@ -115,8 +115,7 @@ struct BoxCursor {
 // keeps a private 24-row table addressed through it.  Classes beyond the 24th present one (rare) go straight to the
 // arena.  (Earlier large-K variants: one CTA-wide [K x 32] table behind shared atomics, 43-57 % of the roofline -- 2 x
 // ~64 LSU cycles per update; a per-warp slot cache with ballot lookups, 44-54 % -- per-quad lookup cost.)
-// RUNLEN (unused) keeps a class run in registers.
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, bool RUNLEN>
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS>
 __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMap* maps, const int K, const int stages,
                                              const int tile, unsigned char* smem) {
   constexpr int kBoxPx = kBoxRowBytes / static_cast<int>(sizeof(T));  // 32 (fp32) / 64 (bf16)
@@ -276,21 +275,6 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   const uint32_t row_off = static_cast<uint32_t>(lane * kBoxRowBytes);
   const uint32_t l7 = static_cast<uint32_t>(lane & 7);
 
-  // run state (RUNLEN only): class of the open run (K = none / dropped) and its partial sums
-  unsigned run_key = static_cast<unsigned>(K);
-  float run1 = 0.f, run2 = 0.f;
-  auto run_add = [&](unsigned key, float a1, float a2) {  // key is warp-uniform: no divergence
-    if (key != run_key) {
-      if (run_key < static_cast<unsigned>(K)) acc_add(run_key, run1, run2);
-      run_key = key;
-      run1 = a1;
-      run2 = a2;
-    } else {
-      run1 += a1;
-      run2 += a2;
-    }
-  };
-
   int stage = 0;
   uint32_t parity = 0;
   for (int it = 0; it < n_my; ++it) {
@@ -318,10 +302,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
         }
         s1a = add2(s1a, s1b);
         s2a = add2(s2a, s2b);
-        if (RUNLEN) run_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
-        else acc_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
-      } else if (RUNLEN) {
-        run_add(static_cast<unsigned>(K), 0.f, 0.f);  // dropped pixels close the open run
+        acc_add(key0, lo2(s1a) + hi2(s1a), lo2(s2a) + hi2(s2a));
       }
     } else {
       // a class boundary crosses the box: per quad (4 px, one packed key word) -- a quad with one
@@ -329,7 +310,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
       // Large-K mode: every lane first translates ITS key word to table rows through the tile's remap (4 byte
       // look-ups per lane per box instead of one look-up per quad in the loop below).
       unsigned rw = lw;
-      if (SHARED_ACC && !RUNLEN) {
+      if (SHARED_ACC) {
         rw = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) rw |= static_cast<unsigned>(remap[(lw >> (8 * e)) & 0xffu]) << (8 * e);
@@ -342,33 +323,22 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
         load_group<T, BWD, AFFINE>(gaddr, sc2, sf2, v);
 #pragma unroll
         for (int h = 0; h < kQuadsPerGroup; ++h) {
-          const unsigned wv = __shfl_sync(0xffffffffu, RUNLEN ? lw : rw, g * kQuadsPerGroup + h);
-          const unsigned key = wv & 0xffu;  // a table row (or, with RUNLEN, a class)
-          if (wv == key * 0x01010101u && (RUNLEN || !SHARED_ACC || key != kOverflow)) {
-            if (RUNLEN) {
-              if (key < static_cast<unsigned>(K)) {
-                const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
-                const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
-                run_add(key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
-              } else {
-                run_add(static_cast<unsigned>(K), 0.f, 0.f);
-              }
-            } else if (key < row_limit) {
+          const unsigned wv = __shfl_sync(0xffffffffu, rw, g * kQuadsPerGroup + h);
+          const unsigned key = wv & 0xffu;  // a table row
+          if (wv == key * 0x01010101u && (!SHARED_ACC || key != kOverflow)) {
+            if (key < row_limit) {
               const f2 t1 = add2(v[2 * h], v[2 * h + 1]);
               const f2 t2 = fma2(v[2 * h + 1], v[2 * h + 1], mul2(v[2 * h], v[2 * h]));
               acc_add_row(acc_lane, key, lo2(t1) + hi2(t1), lo2(t2) + hi2(t2));
             }
           } else {  // straddling quad, or (large-K mode) a quad of overflow classes: pixel by pixel, by class
-            const unsigned kv = SHARED_ACC && !RUNLEN ? __shfl_sync(0xffffffffu, lw, g * kQuadsPerGroup + h) : wv;
+            const unsigned kv = SHARED_ACC ? __shfl_sync(0xffffffffu, lw, g * kQuadsPerGroup + h) : wv;
 #pragma unroll 1
             for (int e = 0; e < 4; ++e) {
               const unsigned ke = (kv >> (8 * e)) & 0xffu;
               if (ke < static_cast<unsigned>(K)) {
                 const float x = load_px<T, BWD, AFFINE>(gaddr + (h * 4 + e) * static_cast<int>(sizeof(T)), sc, sf);
-                if (RUNLEN) run_add(ke, x, x * x);
-                else acc_add(ke, x, x * x);
-              } else if (RUNLEN) {
-                run_add(static_cast<unsigned>(K), 0.f, 0.f);
+                acc_add(ke, x, x * x);
               }
             }
           }
@@ -383,7 +353,6 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
       parity ^= 1u;
     }
   }
-  if (RUNLEN) run_add(static_cast<unsigned>(K), 0.f, 0.f);  // close the last run
   __syncthreads();
 
   // ---- CTA partials -> fp64 arena (coalesced RED.F64; zero partials are skipped) ----------------
@@ -406,7 +375,7 @@ __device__ __forceinline__ void process_tile(const LayerDev& L, const CUtensorMa
   }
 }
 
-template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL, bool RUNLEN>
+template <typename T, bool BWD, bool AFFINE, bool SHARED_ACC, int WARPS, int MAXL>
 __global__ void __launch_bounds__(WARPS * 32, 4)
     class_stats_kernel(const __grid_constant__ GroupParams<MAXL, BWD ? 2 : 1> P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -419,7 +388,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4)
     if (P.tile_prefix[mid] <= tile) lo = mid;
     else hi = mid;
   }
-  process_tile<T, BWD, AFFINE, SHARED_ACC, WARPS, RUNLEN>(P.L[lo], &P.maps[lo * (BWD ? 2 : 1)], P.K, P.stages, tile - P.tile_prefix[lo],
+  process_tile<T, BWD, AFFINE, SHARED_ACC, WARPS>(P.L[lo], &P.maps[lo * (BWD ? 2 : 1)], P.K, P.stages, tile - P.tile_prefix[lo],
                                                   smem);
 }
 
@@ -473,7 +442,7 @@ int launch_tiled(GroupParams<MAXL, BWD ? 2 : 1>& P, int n_tiles, cudaStream_t st
   constexpr int kWarpsT = kWarpsPrivate;
   P.stages = pick_stages();
   const size_t smem = tile_smem_bytes(P.K, BWD, SHARED_ACC, P.stages);
-  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL, false>;
+  auto kern = class_stats_kernel<T, BWD, AFFINE, SHARED_ACC, kWarpsT, MAXL>;
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
   kern<<<n_tiles, kWarpsT * 32, smem, stream>>>(P);
