@@ -398,12 +398,15 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     finally:
         run.close()
     sc = run.scorer
-    out = {"eic": {k: v.cpu() for k, v in sc.eic_dict()["eic"].items()}}
+    flat = sc.eic.cpu()  # ONE device->host copy; the per-layer tensors of score.pth are slices of it
+    out = {"eic": {n: flat[a:b].clone() for n, a, b in zip(sc.names, sc.offsets[:-1], sc.offsets[1:])}}
     d2h += sc.eic.numel() * 4
     if return_class_stats:
-        stats, cnt = sc.class_stats()
-        out["class_stats"] = {k: (a.cpu(), b.cpu()) for k, (a, b) in stats.items()}
-        out["class_counts"] = {k: v.cpu() for k, v in cnt.items()}
+        totals = (sc.totals if sc.totals is not None else sc.step_arena).cpu()
+        cnt = sc.cnt.cpu()
+        out["class_stats"] = {n: (totals[0][:, a:b].clone(), totals[1][:, a:b].clone())
+                              for n, a, b in zip(sc.names, sc.offsets[:-1], sc.offsets[1:])}
+        out["class_counts"] = {r: cnt[i].clone() for i, r in enumerate(sc.resolutions)}
     torch.cuda.synchronize(device)
     out["_stats"] = dict(steps=len(plan), h2d_bytes=h2d, d2h_bytes=d2h, launches=ops.launch_count() - launches0,
                          losses=losses[:len(plan)].clone())
