@@ -286,9 +286,12 @@ class CalibrationRun:
         self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
                                        keep_totals=keep_totals, timing=timing).attach()
         self._saved = None
-        if restore_bn_stats:
-            self._saved = [(m, m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone())
-                           for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.running_mean is not None]
+        if restore_bn_stats:  # train-mode BN updates its running statistics: snapshot them (a few fused launches)
+            bns = [m for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.running_mean is not None]
+            live = [m.running_mean for m in bns] + [m.running_var for m in bns]
+            counters = [m.num_batches_tracked for m in bns]
+            self._saved = (live, torch._foreach_mul(live, 1.0) if live else [], counters,
+                           torch._foreach_add(counters, 0) if counters else [])
         self._was_training = model.training
         model.train()
         self.group = process_group
@@ -324,11 +327,13 @@ class CalibrationRun:
         self.model.train(self._was_training)
         self.model.zero_grad(set_to_none=True)
         if self._saved is not None:
+            live, snap, counters, csnap = self._saved
             with torch.no_grad():
-                for m, mean, var, nbt in self._saved:
-                    m.running_mean.copy_(mean)
-                    m.running_var.copy_(var)
-                    m.num_batches_tracked.copy_(nbt)
+                if live:
+                    torch._foreach_copy_(live, snap)
+                if counters:
+                    torch._foreach_copy_(counters, csnap)
+            self._saved = None
 
 
 def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, flush_bytes=1 << 30,
