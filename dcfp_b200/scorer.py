@@ -337,7 +337,7 @@ class CalibrationRun:
 
 
 def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, flush_bytes=1 << 30,
-                          return_class_stats=False, seed=0, scores_only=False):
+                          return_class_stats=False, seed=0, scores_only=False, channels_last=True):
     """Public end-to-end call: HOST images [n,3,H,W] / labels [n,H,W] -> EIC scores on the host.
 
     Every step copies its micro-batch host->device from pinned memory and reads the step's loss back;
@@ -345,9 +345,17 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     {'eic': {bn_name: FloatTensor[C] (cpu)}, '_stats': {...}} -- `{'eic': ...}` is score.pth's layout."""
     ops.require_gpu()
     device = next(model.parameters()).device
-    # feed the model in its own memory format (channels_last models: NHWC feature maps, K1's NHWC path)
-    nhwc = any(p.dim() == 4 and p.shape[1] > 1 and p.shape[2] * p.shape[3] > 1 and not p.is_contiguous()
-               and p.is_contiguous(memory_format=torch.channels_last) for p in model.parameters())
+    # channels_last is cuDNN's native tensor-core layout (no per-convolution transposes: 52 -> 36 ms per c2 step) and
+    # takes K1's NHWC path.  An NCHW model is converted for the duration of the pass (strides only: parameter VALUES do
+    # not change) and converted back afterwards; channels_last=False scores it as it is.
+    def is_cl(p):
+        return p.dim() == 4 and p.shape[1] > 1 and p.shape[2] * p.shape[3] > 1 and not p.is_contiguous() \
+            and p.is_contiguous(memory_format=torch.channels_last)
+    nhwc = any(is_cl(p) for p in model.parameters())
+    converted = False
+    if channels_last and not nhwc:
+        model.to(memory_format=torch.channels_last)
+        nhwc = converted = True
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     world = torch.distributed.get_world_size() if dist_on else 1
     rank = torch.distributed.get_rank() if dist_on else 0
@@ -402,6 +410,8 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
             run.scorer.all_reduce_totals()
     finally:
         run.close()
+        if converted:
+            model.to(memory_format=torch.contiguous_format)
     sc = run.scorer
     flat = sc.eic.cpu()  # ONE device->host copy; the per-layer tensors of score.pth are slices of it
     out = {"eic": {n: flat[a:b].clone() for n, a, b in zip(sc.names, sc.offsets[:-1], sc.offsets[1:])}}
