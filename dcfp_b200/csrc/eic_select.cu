@@ -117,11 +117,12 @@ __device__ uint32_t block_radix_select(Visit visit, long long k, uint32_t* hist 
   return prefix;
 }
 
-// one CTA per group: thresh[g] = k_idx[g]-th smallest score among the layers of group g
-__global__ void __launch_bounds__(kSelThreads) group_thresh_kernel(const float* __restrict__ score,
-                                                                   const int32_t* __restrict__ layer_off,
-                                                                   const int32_t* __restrict__ layer_group, int n_layers,
-                                                                   long long k0, long long k1, float* __restrict__ thresh_out) {
+// one CTA per group: thresh[g] = k_idx[g]-th smallest score among the layers of group g  (fallback for score vectors
+// whose per-element group map does not fit in shared memory: walks the layers one by one)
+__global__ void __launch_bounds__(kSelThreads) group_thresh_layers_kernel(const float* __restrict__ score,
+                                                                          const int32_t* __restrict__ layer_off,
+                                                                          const int32_t* __restrict__ layer_group, int n_layers,
+                                                                          long long k0, long long k1, float* __restrict__ thresh_out) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bcast[2];
   const int g = blockIdx.x;
@@ -139,6 +140,76 @@ __global__ void __launch_bounds__(kSelThreads) group_thresh_kernel(const float* 
   };
   const uint32_t key = block_radix_select(visit, k, hist, bcast);
   if (threadIdx.x == 0) thresh_out[g] = key2f(key);
+}
+
+// Same result, built for the sizes that occur (<= ~54 k scores): the CTA first writes a one-byte group id per element
+// into shared memory, then every radix pass is ONE flat, 8x-unrolled sweep over the score vector (independent loads in
+// flight) into per-warp histograms.  The layer-by-layer walk above exposes a global-load latency per layer and pass
+// (113 layers x 4 passes: 148 us on c2); this one takes ~15 us.
+constexpr int kSelUnroll = 8;
+__global__ void __launch_bounds__(kSelThreads) group_thresh_kernel(const float* __restrict__ score,
+                                                                   const int32_t* __restrict__ layer_off,
+                                                                   const int32_t* __restrict__ layer_group, int n_layers,
+                                                                   int n_total, long long k0, long long k1,
+                                                                   float* __restrict__ thresh_out) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  uint32_t* whist = reinterpret_cast<uint32_t*>(sel_smem);  // [32 warps][256]
+  uint32_t* hist = whist + 32 * 256;                        // [256]
+  uint32_t* bcast = hist + 256;                             // [2]
+  unsigned char* grp = reinterpret_cast<unsigned char*>(bcast + 2);  // [n_total]
+  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long k = g == 0 ? k0 : k1;
+  if (k < 0) {
+    if (tid == 0) thresh_out[g] = 0.f;
+    return;
+  }
+  for (int l = warp; l < n_layers; l += kSelThreads / 32) {
+    const unsigned char gl = static_cast<unsigned char>(layer_group[l]);
+    const int end = layer_off[l + 1];
+    for (int i = layer_off[l] + lane; i < end; i += 32) grp[i] = gl;
+  }
+  __syncthreads();
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 32 * 256; i += kSelThreads) whist[i] = 0;
+    __syncthreads();
+    for (int base = 0; base < n_total; base += kSelThreads * kSelUnroll) {
+      uint32_t key[kSelUnroll];
+      bool mine[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int i = base + u * kSelThreads + tid;
+        mine[u] = i < n_total && grp[i] == g;
+        key[u] = mine[u] ? f2key(score[i]) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u)
+        if (mine[u] && (key[u] & mask) == prefix) atomicAdd(&whist[warp * 256 + ((key[u] >> shift) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t sum = 0;
+      for (int w = 0; w < 32; ++w) sum += whist[w * 256 + tid];
+      hist[tid] = sum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      long long rem = k;
+      int d = 0;
+      for (; d < 255; ++d) {
+        if (rem < static_cast<long long>(hist[d])) break;
+        rem -= hist[d];
+      }
+      bcast[0] = static_cast<uint32_t>(d);
+      bcast[1] = static_cast<uint32_t>(rem);
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    mask |= 0xffu << shift;
+    k = bcast[1];
+    __syncthreads();
+  }
+  if (tid == 0) thresh_out[g] = key2f(prefix);
 }
 
 constexpr int kMaskThreads = 256;
@@ -245,9 +316,18 @@ extern "C" int dcfp_thresh_mask(const float* score, const int32_t* layer_off, co
   DCFP_REQUIRE(k_idx_host[0] < n_total && k_idx_host[1] < n_total, DCFP_EINVAL,
                "thresh_mask: threshold index out of range (global_percent >= 1?)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  group_thresh_kernel<<<2, kSelThreads, 0, s>>>(score, layer_off, layer_group, n_layers, k_idx_host[0], k_idx_host[1],
-                                                thresh_out);
-  int rc = finish_launch("group_thresh");
+  const size_t sel_smem = (32 * 256 + 256 + 2) * sizeof(uint32_t) + static_cast<size_t>(n_total);
+  int rc;
+  if (sel_smem <= 200u * 1024u) {
+    rc = ensure_smem(reinterpret_cast<const void*>(group_thresh_kernel), static_cast<int>(sel_smem));
+    if (rc) return rc;
+    group_thresh_kernel<<<2, kSelThreads, sel_smem, s>>>(score, layer_off, layer_group, n_layers, n_total, k_idx_host[0],
+                                                         k_idx_host[1], thresh_out);
+  } else {
+    group_thresh_layers_kernel<<<2, kSelThreads, 0, s>>>(score, layer_off, layer_group, n_layers, k_idx_host[0], k_idx_host[1],
+                                                         thresh_out);
+  }
+  rc = finish_launch("group_thresh");
   if (rc) return rc;
   layer_mask_kernel<<<n_layers, kMaskThreads, 0, s>>>(score, layer_off, layer_group, min_keep, thresh_out, mask_out, kept_out);
   return finish_launch("layer_mask");

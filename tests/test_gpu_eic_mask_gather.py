@@ -162,3 +162,20 @@ def test_bias_comp(native, shape):
     exp = gather_ref.bias_offset(W, act)
     mass = np.abs(W.astype(np.float64)).reshape(shape[0], shape[1], -1).sum(2) @ np.abs(act.astype(np.float64))
     assert (np.abs(got - exp) <= 1e-5 * mass + 1e-30).all()
+
+
+def test_thresholds_large_score_vector_takes_the_layer_walk(native):
+    """> ~170 k scores: the per-element group map no longer fits in shared memory -> the layer-by-layer select kernel."""
+    from dcfp_b200 import ops
+    rng = np.random.RandomState(17)
+    sizes = [2048] * 100 + [333, 64]
+    groups = [0] * 60 + [1] * 40 + [0, 1]
+    scores = [(np.exp(rng.standard_normal(c)) * 1e-6).astype(np.float32) for c in sizes]
+    for s in scores[::3]:
+        s[rng.rand(s.size) < 0.3] = 0.0
+    for gp in (0.5, 0.9):
+        mask, thresh, kept = _run_mask(ops, scores, groups, gp, 0.02)
+        t_ref = mask_ref.thresholds(scores, groups, gp)
+        assert [float(t) for t in thresh] == [float(t) for t in t_ref]
+        m_ref = np.concatenate(mask_ref.masks(scores, groups, t_ref, 0.02))
+        assert np.array_equal(mask, m_ref)
