@@ -17,29 +17,46 @@ constexpr int kGatherThreads = 256;
 constexpr int kGatherPerThread = 8;
 constexpr int kGatherTile = kGatherThreads * kGatherPerThread;  // dst elements per CTA
 
-template <typename E>
+// KHW: kernel footprint known at compile time (1 = 1x1 conv / linear / vectors, 9 = 3x3 conv; 0 = runtime value).
+// One 64-bit division per THREAD locates the tile; every element then costs one 32-bit division by the row length and
+// one by KHW (a multiply-shift when KHW is a constant) -- the first version divided 64-bit values twice per element and
+// ran at a quarter of the HBM roofline.
+template <typename E, int KHW>
 __device__ __forceinline__ void gather_tile(const dcfp_gather_desc& d, long long first) {
-  const long long row = static_cast<long long>(d.n_in) * d.khw;  // dst elements per output channel
-  const long long total = row * d.n_out;
+  const int khw = KHW ? KHW : d.khw;
+  const unsigned row = static_cast<unsigned>(d.n_in) * static_cast<unsigned>(khw);  // dst elements per output channel
+  const long long total = static_cast<long long>(row) * d.n_out;
   const E* __restrict__ src = static_cast<const E*>(d.src);
   E* __restrict__ dst = static_cast<E*>(d.dst);
-  const long long src_row = static_cast<long long>(d.I) * d.khw;
+  const long long src_row = static_cast<long long>(d.I) * khw;
+  const long long o_first = first / row;
+  const unsigned r_first = static_cast<unsigned>(first - o_first * row);
 #pragma unroll
   for (int u = 0; u < kGatherPerThread; ++u) {
-    const long long t = first + u * kGatherThreads + threadIdx.x;
+    const unsigned local = u * kGatherThreads + threadIdx.x;
+    const long long t = first + local;
     if (t >= total) break;
-    const int o = static_cast<int>(t / row);
-    const int rem = static_cast<int>(t - o * row);
-    const int i = rem / d.khw, e = rem - i * d.khw;
+    const unsigned r = r_first + local;  // < row + tile: fits in 32 bits (row < 2^31, checked on the host)
+    const unsigned q = r / row;
+    const unsigned rem = r - q * row;
+    const int o = static_cast<int>(o_first) + static_cast<int>(q);
+    const unsigned i = rem / static_cast<unsigned>(khw), e = rem - i * static_cast<unsigned>(khw);
     const int so = d.out_idx ? d.out_idx[o] : o;
-    const int si = d.in_idx ? d.in_idx[i] : i;
-    dst[t] = src[so * src_row + static_cast<long long>(si) * d.khw + e];
+    const int si = d.in_idx ? d.in_idx[i] : static_cast<int>(i);
+    dst[t] = src[so * src_row + static_cast<long long>(si) * khw + e];
   }
 }
 
 template <typename E>
+__device__ __forceinline__ void gather_tile_any(const dcfp_gather_desc& d, long long first) {
+  if (d.khw == 1) gather_tile<E, 1>(d, first);  // CTA-uniform branch
+  else if (d.khw == 9) gather_tile<E, 9>(d, first);
+  else gather_tile<E, 0>(d, first);
+}
+
+template <typename E>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const dcfp_gather_desc d) {
-  gather_tile<E>(d, static_cast<long long>(blockIdx.x) * kGatherTile);
+  gather_tile_any<E>(d, static_cast<long long>(blockIdx.x) * kGatherTile);
 }
 
 template <typename E>
@@ -52,7 +69,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_grouped_kernel(const dc
     if (tile_prefix[mid] <= tile) lo = mid;
     else hi = mid;
   }
-  gather_tile<E>(descs[lo], (tile - tile_prefix[lo]) * kGatherTile);
+  gather_tile_any<E>(descs[lo], (tile - tile_prefix[lo]) * kGatherTile);
 }
 
 // offset[o] = sum_i act[i] * sum_e W[o][i][e]; one CTA per output channel streams the row with coalesced loads
@@ -85,6 +102,8 @@ int validate_gather(const dcfp_gather_desc& d, int idx) {
   const bool empty = d.n_out == 0 || d.n_in == 0;
   DCFP_REQUIRE(empty || (d.src && d.dst), DCFP_EINVAL, "channel_gather[%d]: null src/dst", idx);
   DCFP_REQUIRE(d.in_idx != nullptr || d.n_in == d.I, DCFP_EINVAL, "channel_gather[%d]: in_idx NULL requires n_in == I", idx);
+  DCFP_REQUIRE(static_cast<long long>(d.n_in) * d.khw < (1LL << 31) - kGatherTile, DCFP_ETOOBIG,
+               "channel_gather[%d]: output row too long", idx);
   return 0;
 }
 
