@@ -31,20 +31,29 @@ __device__ __forceinline__ void gather_tile(const dcfp_gather_desc& d, long long
   const long long src_row = static_cast<long long>(d.I) * khw;
   const long long o_first = first / row;
   const unsigned r_first = static_cast<unsigned>(first - o_first * row);
+  // phase 1: all index math and all loads (independent, predicated -- no early exit, so they are in flight together);
+  // phase 2: the coalesced stores
+  E v[kGatherPerThread];
+  bool ok[kGatherPerThread];
 #pragma unroll
   for (int u = 0; u < kGatherPerThread; ++u) {
     const unsigned local = u * kGatherThreads + threadIdx.x;
-    const long long t = first + local;
-    if (t >= total) break;
-    const unsigned r = r_first + local;  // < row + tile: fits in 32 bits (row < 2^31, checked on the host)
-    const unsigned q = r / row;
-    const unsigned rem = r - q * row;
-    const int o = static_cast<int>(o_first) + static_cast<int>(q);
-    const unsigned i = rem / static_cast<unsigned>(khw), e = rem - i * static_cast<unsigned>(khw);
-    const int so = d.out_idx ? d.out_idx[o] : o;
-    const int si = d.in_idx ? d.in_idx[i] : static_cast<int>(i);
-    dst[t] = src[so * src_row + static_cast<long long>(si) * khw + e];
+    ok[u] = first + local < total;
+    v[u] = E(0);
+    if (ok[u]) {
+      const unsigned r = r_first + local;  // < row + tile: fits in 32 bits (row < 2^31 - tile, checked on the host)
+      const unsigned q = r / row;
+      const unsigned rem = r - q * row;
+      const int o = static_cast<int>(o_first) + static_cast<int>(q);
+      const unsigned i = rem / static_cast<unsigned>(khw), e = rem - i * static_cast<unsigned>(khw);
+      const int so = d.out_idx ? __ldg(d.out_idx + o) : o;
+      const int si = d.in_idx ? __ldg(d.in_idx + i) : static_cast<int>(i);
+      v[u] = src[so * src_row + static_cast<long long>(si) * khw + e];
+    }
   }
+#pragma unroll
+  for (int u = 0; u < kGatherPerThread; ++u)
+    if (ok[u]) dst[first + u * kGatherThreads + threadIdx.x] = v[u];
 }
 
 template <typename E>
