@@ -239,3 +239,30 @@ def test_nchw_model_is_scored_in_channels_last_and_restored(native):
     vb = np.concatenate([v.numpy() for v in b["eic"].values()])
     close = np.abs(va - vb) <= 1e-1 * np.abs(vb) + 1e-1 * np.abs(vb).mean()
     assert close.mean() > 0.95, close.mean()
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_bf16_feature_maps_under_autocast(native, channels_last):
+    """Under bf16 autocast the conv outputs -- the BN inputs K1 reads -- and their gradients are bf16: K1's bf16 paths
+    (both layouts) must still reproduce autograd's BN-gamma gradient (both accumulate the same bf16 values in fp32)."""
+    from dcfp_b200.scorer import CalibrationRun
+    model = _setup()
+    x, y = _batch([0, 1], valid_only=True)
+    x, y = x.to(DEV), y.to(DEV)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    seen = {}
+    bn = model.get_submodule("backbone.layer2.0.bn1")
+    h = bn.register_forward_hook(lambda m, i, o: seen.__setitem__("dtype", i[0].dtype))
+    run = CalibrationRun(model, K, r=0.999, seed=3)
+    with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+        run.step(x, y, mb_index=0)
+    h.remove()
+    assert seen["dtype"] == torch.bfloat16
+    sc = run.scorer
+    S1 = sc.totals[0].sum(0).cpu().numpy()
+    g = torch.cat([m.weight.grad.detach().float().reshape(-1) for _, m in sc.layers]).cpu().numpy()
+    ok = _close(S1, g, 2e-2)
+    assert ok.mean() > 0.995, "%d of %d channels off" % ((~ok).sum(), ok.size)
+    run.close()
