@@ -243,26 +243,42 @@ def test_nchw_model_is_scored_in_channels_last_and_restored(native):
 
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_bf16_feature_maps_under_autocast(native, channels_last):
-    """Under bf16 autocast the conv outputs -- the BN inputs K1 reads -- and their gradients are bf16: K1's bf16 paths
-    (both layouts) must still reproduce autograd's BN-gamma gradient (both accumulate the same bf16 values in fp32)."""
+    """Under bf16 autocast the conv outputs -- the BN inputs K1 reads -- and their gradients are bf16.  K1's bf16 paths
+    (both layouts) are checked (a) tightly against the fp64 oracle on the captured bf16 tensors of one layer and (b)
+    loosely against autograd's BN-gamma gradient (cuDNN's bf16 batch-norm backward is itself only bf16-accurate on
+    channels whose gradient cancels: ~0.5 % of the channels differ by more than 2 %)."""
     from dcfp_b200.scorer import CalibrationRun
     model = _setup()
     x, y = _batch([0, 1], valid_only=True)
-    x, y = x.to(DEV), y.to(DEV)
+    xd, yd = x.to(DEV), y.to(DEV)
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
-        x = x.contiguous(memory_format=torch.channels_last)
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    target = "backbone.layer2.0.bn1"
+    bn = model.get_submodule(target)
     seen = {}
-    bn = model.get_submodule("backbone.layer2.0.bn1")
-    h = bn.register_forward_hook(lambda m, i, o: seen.__setitem__("dtype", i[0].dtype))
+
+    def grab(m, i, o):
+        seen["x"] = i[0].detach().clone()
+        o.register_hook(lambda g: seen.__setitem__("dy", g.detach().clone()))
+
+    h = bn.register_forward_hook(grab)
     run = CalibrationRun(model, K, r=0.999, seed=3)
     with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
-        run.step(x, y, mb_index=0)
+        run.step(xd, yd, mb_index=0)
     h.remove()
-    assert seen["dtype"] == torch.bfloat16
+    assert seen["x"].dtype == torch.bfloat16 and seen["dy"].dtype == torch.bfloat16
     sc = run.scorer
-    S1 = sc.totals[0].sum(0).cpu().numpy()
+    stats, _ = sc.class_stats()
+    xs, dy = seen["x"].float().cpu(), seen["dy"].float().cpu()
+    mean = xs.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(xs.var(dim=(0, 2, 3), unbiased=False) + bn.eps)
+    _, r1, r2 = class_stats_ref.class_stats_bwd(xs, dy, mean, invstd, y, K)
+    mass = class_stats_ref.abs_mass(class_stats_ref.functor_bwd(xs, dy, invstd, -mean * invstd), y, K)
+    S1 = stats[target][0].cpu()
+    assert ((S1 - r1).abs() <= 1e-4 * mass + 1e-30).all(), ((S1 - r1).abs() / (mass + 1e-30)).max()
+    tot = sc.totals[0].sum(0).cpu().numpy()
     g = torch.cat([m.weight.grad.detach().float().reshape(-1) for _, m in sc.layers]).cpu().numpy()
-    ok = _close(S1, g, 2e-2)
-    assert ok.mean() > 0.995, "%d of %d channels off" % ((~ok).sum(), ok.size)
+    ok = _close(tot, g, 2e-2)
+    assert ok.mean() > 0.98, "%d of %d channels off" % ((~ok).sum(), ok.size)
     run.close()
