@@ -62,6 +62,8 @@ def parse_args():
     p.add_argument("--scores-only", action="store_true",
                    help="freeze every non-BN parameter during scoring: no weight-gradient convolutions (the scores do not "
                         "need them); default off = the reference's full backward")
+    p.add_argument("--no-forward-functor", action="store_true",
+                   help="skip the extra forward-only region (north_star-literal statistics: K1 with v = BN output)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock cap of the reference arm")
@@ -330,9 +332,36 @@ def run_b200_arm(args, c):
     arena_bytes = sc.total_arena.numel() * 8
     sum_c = sc.total_channels
     run.close()
-    del run, sc, resident
-    torch.cuda.empty_cache()
+    del run, sc
     value = K * mb * world / (ms_a * 1e-3)
+
+    # ---- forward functor (north_star-literal): forward pass only, K1 with v = BN output, deferred into grouped launches
+    forward = None
+    if not args.no_forward_functor:
+        run_f = CalibrationRun(model, c["num_classes"], mode="fwd", flush_bytes=args.flush_mb << 20, keep_totals=True, timing=True, seed=0)
+        for s in range(max(W, 1)):
+            run_f.step(*resident[s], mb_index=s * world + rank)
+        barrier()
+        run_f.scorer.k1_events.clear()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for s in range(W, W + K):
+            run_f.step(*resident[s], mb_index=s * world + rank)
+        f1.record()
+        barrier()
+        ms_f = max_over_ranks(f0.elapsed_time(f1))
+        fk_ms, fk_bytes, fk_launches = run_f.scorer.k1_time_ms()
+        run_f.close()
+        peak_f, _ = hbm_peak()
+        forward = {"what": "forward pass + class statistics of every scored BN OUTPUT (v = y, pre-ReLU), inputs resident in HBM",
+                   "value": K * mb * world / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / K,
+                   "k1_achieved_gbs": fk_bytes / (fk_ms * 1e-3) / 1e9 if fk_ms > 0 else None,
+                   "k1_frac_of_hbm_peak": (fk_bytes / (fk_ms * 1e-3) / 1e9 / peak_f) if fk_ms > 0 else None,
+                   "k1_launches": fk_launches, "k1_algorithmic_bytes_per_image": fk_bytes / (K * mb),
+                   "k1_images_per_s_of_kernel_time": K * mb / (fk_ms * 1e-3) if fk_ms > 0 else None}
+        del run_f
+    del resident
+    torch.cuda.empty_cache()
 
     # ---- phase B: public host API, H2D + D2H inside the timed region -----------------------------------------
     e2e = None
@@ -397,7 +426,7 @@ def run_b200_arm(args, c):
                                        "fold -> all-reduce(dgamma)/N -> EIC update; no optimizer step",
                            "l2": "per-step feature maps (%.1f GB read by K1) exceed the 126 MB L2; no explicit flush" % (k1_bytes / K / 1e9),
                            "layout": args.layout, "backward": "scores_only (no weight-gradient convolutions)" if args.scores_only else "full (all gradients, as the reference's training step)", "k1_flush_mib": args.flush_mb, "priming_steps": args.prime, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
-                "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "forward_functor": forward, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K,sumC] fp64 totals + counts at the end of the pass"}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -92,6 +92,7 @@ class ClassStatsScorer:
         self._handles = []
         self.flush_bytes = int(flush_bytes)
         self._pending = []
+        self._pending_fwd = []
         self._pending_bytes = 0
         self.eic = torch.zeros(C, dtype=torch.float32, device=self.device)
         self._gamma = None
@@ -110,7 +111,7 @@ class ClassStatsScorer:
         for h in self._handles:
             h.remove()
         self._handles = []
-        self._pending, self._pending_bytes = [], 0
+        self._pending, self._pending_fwd, self._pending_bytes = [], [], 0
 
     def set_labels(self, labels):
         """labels of the micro-batch about to run: [N, H0, W0] uint8 / int32 / int64 on the device."""
@@ -140,17 +141,44 @@ class ClassStatsScorer:
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
         bwd = items[0][1] is not None
+        affine = items[0][2] is not None
         ops.class_stats_grouped([i[0] for i in items], [i[4] for i in items], self.K, [i[5] for i in items], [i[6] for i in items],
                                 dys=[i[1] for i in items] if bwd else None,
-                                scales=[i[2] for i in items] if bwd else None, shifts=[i[3] for i in items] if bwd else None,
+                                scales=[i[2] for i in items] if affine else None, shifts=[i[3] for i in items] if affine else None,
                                 affine_mode=ops.AFFINE_INVSTD_MEAN if bwd else ops.AFFINE_SCALE_SHIFT)
         if self.timing:
             e1.record()
             self.k1_events.append((e0, e1, nbytes))
         self.k1_bytes += nbytes
 
+    def _flush_fwd(self):
+        """Deferred forward functor: y = (x - mean) * invstd * gamma + beta = x * scale + shift with the per-channel
+        scale / shift of ALL pending layers computed by four small launches on the concatenated vectors."""
+        items = self._pending_fwd
+        self._pending_fwd = []
+        with torch.no_grad():
+            mean = torch.cat([i[1] for i in items])
+            invstd = torch.cat([i[2] for i in items])
+            gamma = torch.cat([i[3].detach().float() for i in items])
+            beta = torch.cat([i[4].detach().float() for i in items])
+            scale = invstd * gamma
+            shift = beta - mean * scale
+        launch, pos = [], 0
+        for xd, m, _, _, _, keys, S1, S2 in items:
+            c = m.numel()
+            launch.append((xd, None, scale[pos:pos + c], shift[pos:pos + c], keys, S1, S2))
+            pos += c
+        groups = {}
+        for it in launch:
+            groups.setdefault((it[0].dtype, it[0].is_contiguous()), []).append(it)
+        for its in groups.values():
+            self._launch(its)
+
     def flush(self):
-        """Reduce every pending (deferred) backward-mode layer; grouped by (dtype, layout) as one launch needs."""
+        """Reduce every pending (deferred) layer; grouped by (dtype, layout) as one launch needs."""
+        if self._pending_fwd:
+            self._pending_bytes = 0
+            self._flush_fwd()
         if not self._pending:
             return
         groups = {}
@@ -169,6 +197,25 @@ class ClassStatsScorer:
                 return
             x = inputs[0]
             if self.mode == "fwd":
+                # v = y (the BN output, pre-ReLU).  The in-place ReLU that follows overwrites y, so either reduce it
+                # right here (one launch per layer), or -- when autograd recorded the batch statistics -- DEFER: keep
+                # (x, mean, invstd) and let ONE grouped launch at the end of the forward pass evaluate
+                # y = (x - mean) * invstd * gamma + beta inside K1's value functor.
+                node = output.grad_fn if (self.flush_bytes > 0 and torch.is_grad_enabled()) else None
+                mean = getattr(node, "_saved_result1", None) if node is not None else None
+                invstd = getattr(node, "_saved_result2", None) if node is not None else None
+                del node
+                training = module.training or module.running_mean is None
+                if self.flush_bytes > 0 and not training:
+                    mean, invstd = module.running_mean.float(), torch.rsqrt(module.running_var.float() + module.eps)
+                if mean is not None and invstd is not None and mean.numel() == x.shape[1] and mean.dtype == torch.float32:
+                    xd = self._dense(x.detach())
+                    self._pending_fwd.append((xd, mean, invstd, module.weight, module.bias,
+                                              self._keys_for(xd.shape[2], xd.shape[3]), S1, S2))
+                    self._pending_bytes += xd.numel() * xd.element_size()
+                    if self._pending_bytes >= self.flush_bytes:
+                        self.flush()
+                    return
                 y = self._dense(output.detach())
                 self._launch([(y, None, None, None, self._keys_for(y.shape[2], y.shape[3]), S1, S2)])
                 return

@@ -111,14 +111,34 @@ def test_forward_mode_class_statistics(native):
     captured = {}
     h = bn.register_forward_hook(lambda m, i, o: captured.__setitem__("y", o.detach().clone()))
     run = CalibrationRun(model, K, mode="fwd")
-    with torch.no_grad():
+    with torch.no_grad():  # no autograd: the hook reduces y on the spot (one launch per layer)
         run.step(x.to(DEV), y.to(DEV))
-    h.remove()
     stats, cnt = run.scorer.class_stats()
     rc, r1, r2 = class_stats_ref.class_stats_fwd(captured["y"].cpu(), y, K)
     mass = class_stats_ref.abs_mass(captured["y"].cpu(), y, K)
     S1, S2 = stats[target]
     assert ((S1.cpu() - r1).abs() <= 1e-5 * mass + 1e-30).all() and ((S2.cpu() - r2).abs() <= 1e-5 * r2 + 1e-30).all()
+    n_immediate = run.scorer.k1_bytes
+    run.close()
+    # with autograd on, the batch statistics are known: the layers are DEFERRED into one grouped launch that evaluates
+    # y = (x - mean) * invstd * gamma + beta in the value functor -- same statistics (y itself is recomputed in fp32)
+    with torch.no_grad():
+        for m in model.modules():  # non-trivial affine parameters
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    run = CalibrationRun(model, K, mode="fwd", timing=True)
+    run.step(x.to(DEV), y.to(DEV))
+    h.remove()
+    torch.cuda.synchronize()
+    assert len(run.scorer.k1_events) <= 3, "deferred: a couple of grouped launches, not one per layer"
+    stats, _ = run.scorer.class_stats()
+    yy = captured["y"].cpu()
+    rc, r1, r2 = class_stats_ref.class_stats_fwd(yy, y, K)
+    mass = class_stats_ref.abs_mass(yy, y, K)
+    S1, S2 = stats[target]
+    assert ((S1.cpu() - r1).abs() <= 2e-5 * mass + 1e-30).all() and ((S2.cpu() - r2).abs() <= 1e-4 * r2 + 1e-30).all()
+    assert run.scorer.k1_bytes == n_immediate
     run.close()
 
 
