@@ -305,6 +305,10 @@ class ChannelPruner:
         if topo is None:
             topo = self._trace(supernet, name2module)
             _TOPOLOGY_CACHE[key] = topo
+        else:
+            # the reference traces every time and its pseudo image comes from the GLOBAL torch generator (:191); draw
+            # the same numbers so that RNG-dependent callers (RandomChannelPruner) see the reference's stream
+            torch.randn(*self.trace_input_size)
         for module in name2module.values():
             self.add_pruning_attrs(module)
 

@@ -162,3 +162,21 @@ def test_meta_flops_counter_equals_reference_counter(cfg):
         exp_s = ref_info(model, (3, 256, 256), print_per_layer_stat=False)
     assert flops.model_cost(model, (3, 256, 256)) == exp
     assert flops.get_model_complexity_info(model, (3, 256, 256)) == exp_s
+
+
+def test_random_pruner_live_reference_same_rng_stream():
+    """RandomChannelPruner vs the reference's on the same global-RNG seed -- twice, so that the second call of the
+    product runs from its topology cache and must still consume the generator like the reference's re-trace does."""
+    ref = ref_compat.load_reference()
+    from dcfp_b200.pruners.random_pruner import RandomChannelPruner
+    base = gu.build_model("c1")
+    for seed in (9, 10):
+        torch.manual_seed(seed)
+        pr = ref.rp.RandomChannelPruner(global_percent=0.7, layer_keep=0.02)
+        sa, ca = pr.prune_model(copy.deepcopy(base), except_start_keys=["conv_deepsup"])
+        with oracle_backend():
+            torch.manual_seed(seed)
+            pm = RandomChannelPruner(global_percent=0.7, layer_keep=0.02)
+            sb, cb = pm.prune_model(copy.deepcopy(base), except_start_keys=["conv_deepsup"])
+        assert all(np.array_equal(ca[k]["out_mask"], cb[k]["out_mask"]) for k in ca)
+        assert all(torch.equal(v, sb.state_dict()[k]) for k, v in sa.state_dict().items())
