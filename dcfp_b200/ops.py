@@ -11,19 +11,41 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OPS_LIB = os.path.join(HERE, "lib", "dcfp_torch_ops.so")
 
 _loaded = False
+#: DCFP_NVTX=1 wraps every call into this library in an NVTX range (dcfp::<op>) for nsys / ncu --nvtx timelines
+_NVTX = os.environ.get("DCFP_NVTX", "0") == "1"
+
+
+class _Nvtx:
+    """Proxy over torch.ops.dcfp that brackets each op call with an NVTX range."""
+
+    def __init__(self, ns):
+        self._ns = ns
+
+    def __getattr__(self, name):
+        fn = getattr(self._ns, name)
+
+        def wrapped(*a, **kw):
+            torch.cuda.nvtx.range_push("dcfp::" + name)
+            try:
+                return fn(*a, **kw)
+            finally:
+                torch.cuda.nvtx.range_pop()
+
+        return wrapped
+
 
 
 def load():
     """Registers torch.ops.dcfp.* (idempotent)."""
     global _loaded
     if _loaded:
-        return torch.ops.dcfp
+        return _Nvtx(torch.ops.dcfp) if _NVTX else torch.ops.dcfp
     if not os.path.exists(OPS_LIB):
         raise RuntimeError("dcfp_b200 native library not built: %s is missing. Run `python -m dcfp_b200.build` "
                            "(nvcc, sm_100a). There is no CPU or eager fallback." % OPS_LIB)
     torch.ops.load_library(OPS_LIB)
     _loaded = True
-    return torch.ops.dcfp
+    return _Nvtx(torch.ops.dcfp) if _NVTX else torch.ops.dcfp
 
 
 def require_gpu():
