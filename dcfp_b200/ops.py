@@ -55,10 +55,6 @@ def require_gpu():
     return load()
 
 
-#: set by the CPU test-suite when it swaps the kernels for the oracle to exercise host logic
-BACKEND_OVERRIDDEN = False
-
-
 def device():
     """The CUDA device product code stages tensors on."""
     return torch.device("cuda", torch.cuda.current_device())

@@ -444,7 +444,6 @@ class ChannelPruner:
         (reference :873-905): offset = W.sum((2,3)) @ relu((1 - in_mask) * beta_parent), subtracted
         from the next BN's running_mean (or added to the conv bias).  The reduce-GEMV runs on the GPU;
         when no pruned channel has beta > 0 the offset is exactly zero and nothing is launched."""
-        device = ops.device() if torch.cuda.is_available() or ops.BACKEND_OVERRIDDEN else None
         for name, module in supernet.named_modules():
             if name not in self.modules_have_ancest:
                 continue
@@ -453,6 +452,7 @@ class ChannelPruner:
             activation = torch.relu((1 - sub_module.in_mask) * bias.detach())
             if bool((activation != 0).any()):
                 ops.require_gpu()
+                device = ops.device()
                 w = module.weight.data
                 offset = ops.bias_comp(w.to(device).contiguous(), activation.reshape(-1).to(device=device, dtype=torch.float32))
                 offset = offset.to(w.device)

@@ -55,7 +55,7 @@ def _eic_update(grads, gammas, offsets, eic, r, first_step):
 
 @contextlib.contextmanager
 def oracle_backend():
-    names = ["require_gpu", "device", "thresh_mask", "channel_gather_grouped", "bias_comp", "eic_update", "BACKEND_OVERRIDDEN"]
+    names = ["require_gpu", "device", "thresh_mask", "channel_gather_grouped", "bias_comp", "eic_update"]
     saved = {n: getattr(ops, n) for n in names}
     ops.require_gpu = lambda: None
     ops.device = lambda: torch.device("cpu")
@@ -63,7 +63,6 @@ def oracle_backend():
     ops.channel_gather_grouped = _gather_grouped
     ops.bias_comp = _bias_comp
     ops.eic_update = _eic_update
-    ops.BACKEND_OVERRIDDEN = True
     try:
         yield
     finally:
