@@ -86,6 +86,46 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 
 constexpr int kSelThreads = 1024;
 
+// Picks the digit d with  sum(hist[0..d-1]) <= k < sum(hist[0..d])  and the remainder k - sum(hist[0..d-1]).
+// Executed by warp 0: lane j owns bins 8j..8j+7, an exclusive prefix over the lane sums locates the lane, the lane
+// walks its 8 bins (a single thread walking 256 bins cost ~8 k cycles per radix pass).
+__device__ __forceinline__ void pick_digit(const uint32_t* hist, long long k, uint32_t* bcast) {
+  const int lane = threadIdx.x & 31;
+  uint32_t b[8];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    b[i] = hist[8 * lane + i];
+    mine += b[i];
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const long long excl = static_cast<long long>(incl) - mine;
+  const bool here = k >= excl && k < static_cast<long long>(incl);
+  const unsigned vote = __ballot_sync(0xffffffffu, here);
+  if (vote == 0) {  // k beyond the population (cannot happen for a valid k): clamp to the last bin like the serial walk
+    if (lane == 31) {
+      bcast[0] = 255u;
+      bcast[1] = static_cast<uint32_t>(k - (static_cast<long long>(incl) - b[7]));
+    }
+    return;
+  }
+  if (here) {
+    long long rem = k - excl;
+    int d = 0;
+    for (; d < 7; ++d) {
+      if (rem < static_cast<long long>(b[d])) break;
+      rem -= b[d];
+    }
+    bcast[0] = static_cast<uint32_t>(8 * lane + d);
+    bcast[1] = static_cast<uint32_t>(rem);
+  }
+}
+
 // Block-wide exact k-th smallest key (0-based) among the elements enumerated by `visit`.
 // visit(f) calls f(key) for every element owned by this thread.  4 MSB-first 8-bit passes.
 template <typename Visit>
@@ -98,16 +138,7 @@ __device__ uint32_t block_radix_select(Visit visit, long long k, uint32_t* hist 
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
     });
     __syncthreads();
-    if (threadIdx.x == 0) {
-      long long rem = k;
-      int d = 0;
-      for (; d < 255; ++d) {
-        if (rem < static_cast<long long>(hist[d])) break;
-        rem -= hist[d];
-      }
-      bcast[0] = static_cast<uint32_t>(d);
-      bcast[1] = static_cast<uint32_t>(rem);
-    }
+    if (threadIdx.x < 32) pick_digit(hist, k, bcast);
     __syncthreads();
     prefix |= bcast[0] << shift;
     mask |= 0xffu << shift;
@@ -193,16 +224,7 @@ __global__ void __launch_bounds__(kSelThreads) group_thresh_kernel(const float* 
       hist[tid] = sum;
     }
     __syncthreads();
-    if (tid == 0) {
-      long long rem = k;
-      int d = 0;
-      for (; d < 255; ++d) {
-        if (rem < static_cast<long long>(hist[d])) break;
-        rem -= hist[d];
-      }
-      bcast[0] = static_cast<uint32_t>(d);
-      bcast[1] = static_cast<uint32_t>(rem);
-    }
+    if (tid < 32) pick_digit(hist, k, bcast);
     __syncthreads();
     prefix |= bcast[0] << shift;
     mask |= 0xffu << shift;
