@@ -96,8 +96,10 @@ typedef struct dcfp_layer_desc {
  * forward functor; the backward functor restates the dgamma reduction of
  * autograd's BN backward that feeds pruners/dcfp_pruner.py:18.                              */
 int dcfp_class_stats(const dcfp_layer_desc* desc_host, void* stream);
-/* Same, for up to DCFP_MAX_GROUP_LAYERS resident feature maps in ONE launch (all K, dtype,
- * dy-nullness must agree).  Layers only share the grid; outputs stay per layer.              */
+/* Same, for up to DCFP_MAX_GROUP_LAYERS resident feature maps per call (all K, dtype, dy-nullness
+ * must agree; layouts may mix).  The layers of one layout share ONE launch -- as many as the tensor
+ * maps + layer table fit in kernel parameter space (80..160, more are split transparently); tiny or
+ * unaligned maps take one small launch each.  Layers only share the grid; outputs stay per layer. */
 int dcfp_class_stats_grouped(const dcfp_layer_desc* descs_host, int n_layers, void* stream);
 
 /* ---- K2a: EIC update -- pruners/dcfp_pruner.py:15-20 ------------------------------------------
