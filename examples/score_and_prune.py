@@ -13,6 +13,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from dcfp_b200.pruners import formats
 from dcfp_b200.pruners.search import prune_to_flops_ratio
 from dcfp_b200.scorer import score_calibration_set
 from dcfp_b200.workloads.segnets import CONFIGS, build_segnet
@@ -35,13 +36,15 @@ def main():
     torch.cuda.synchronize()
     print("scored %d images in %.2f s (%d kernels of this library)" % (a.images, time.time() - t, out["_stats"]["launches"]))
     score = os.path.join(a.out, "score.pth")
-    torch.save({"eic": out["eic"]}, score)
+    formats.save_score(out["eic"], score)
     model.criterion = None
     t = time.time()
     sub, channel_cfg, gp = prune_to_flops_ratio(model.cpu(), score, prune_ratio=a.prune_ratio)
     print("pruned at global_percent %.2f in %.2f s" % (gp, time.time() - t))
-    torch.save(sub.state_dict(), os.path.join(a.out, "pruned.pth"))
-    torch.save(channel_cfg, os.path.join(a.out, "channel_cfg.pth"))
+    formats.save_pruned(sub, channel_cfg, a.out)
+    # what a consumer does (prune.py:100-110, train.py:200-207): fresh model -> channel_cfg sizes -> pruned weights
+    fresh = build_segnet(c["arch"], c["backbone"], c["num_classes"], seed=1)
+    formats.load_pruned_model(fresh, os.path.join(a.out, "channel_cfg.pth"), os.path.join(a.out, "pruned.pth"))
     kept = sum(v["out_channels"] for v in channel_cfg.values())
     raw = sum(v["raw_out_channels"] for v in channel_cfg.values())
     print("kept %d of %d output channels; wrote %s" % (kept, raw, a.out))
