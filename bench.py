@@ -274,6 +274,7 @@ def run_b200_arm(args, c):
     # caching allocator would garbage-collect inside timed steps.  Release them once; steady state needs ~20 GB.
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)  # "allocated_peak_gb" below = warm-up + timed steps, not the autotuning trials
     # the EIC state must not see the priming steps: restart the accumulator
     sc.steps = 0
     sc.eic.zero_()
