@@ -11,10 +11,15 @@ class of each pixel (north_star "class-conditional calibration statistics"):
   mode "bwd":  v = dy * xhat   -> sum_k S1[k, c] == bn.weight.grad  (reference-exact EIC feed)
   mode "fwd":  v = BN output y -> class-conditional mean / variance of the feature map
 
-HBM layout: all layers write into ONE fp64 *step arena* [2, K, sumC] (S1 rows,
+Pixels whose label is outside [0, K) -- the ignore label 255 -- carry no loss but DO carry gradient at every layer
+below the logits (receptive fields overlap them), and autograd's bn.weight.grad sums over them.  They are therefore
+not discarded: the arenas hold K + 1 rows, row K collecting those pixels, so that the sum over all rows is the
+reference's gradient exactly while rows [0, K) stay the class-conditional statistics (K <= 254).
+
+HBM layout: all layers write into ONE fp64 *step arena* [2, K+1, sumC] (S1 rows,
 then S2 rows; layer l owns columns [off_l, off_l + C_l)), so that
   * the end-of-step fold (dgamma = sum_k S1, totals += step, step = 0) is one launch,
-  * the multi-GPU combine is one all-reduce of the *total arena* [2, K, sumC] + cnt [R, K].
+  * the multi-GPU combine is one all-reduce of the *total arena* [2, K+1, sumC] + cnt [R, K].
 Backward-mode launches are DEFERRED: the hook only records (x, dy, mean, invstd) -- tensors autograd
 holds anyway, or that live for microseconds otherwise -- and `flush()` reduces every pending layer
 in ONE grouped K1 launch once `flush_bytes` of feature maps are pending (180 GB of HBM make holding a
@@ -78,11 +83,14 @@ class ClassStatsScorer:
             self.offsets.append(self.offsets[-1] + s)
         self.total_channels = self.offsets[-1]
         K, C = self.K, self.total_channels
-        self.step_arena = torch.zeros(2, K, C, dtype=torch.float64, device=self.device)
+        if not 1 <= K <= 254:
+            raise ValueError("num_classes must be in [1, 254] (uint8 class keys, one more row for pixels outside [0, K))")
+        R = self.rows = K + 1  # row K: pixels whose label is outside [0, K) (ignore label)
+        self.step_arena = torch.zeros(2, R, C, dtype=torch.float64, device=self.device)
         # pass-wide totals and pixel counts share one buffer: ONE all-reduce combines everything
-        self.total_arena = torch.zeros(2 * K * C + MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device) if keep_totals else None
-        self.totals = self.total_arena[:2 * K * C].view(2, K, C) if keep_totals else None
-        self.cnt = (self.total_arena[2 * K * C:] if keep_totals else
+        self.total_arena = torch.zeros(2 * R * C + MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device) if keep_totals else None
+        self.totals = self.total_arena[:2 * R * C].view(2, R, C) if keep_totals else None
+        self.cnt = (self.total_arena[2 * R * C:] if keep_totals else
                     torch.zeros(MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device)).view(MAX_RESOLUTIONS, K)
         self._views = {n: (self.step_arena[0][:, a:b], self.step_arena[1][:, a:b])
                        for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
@@ -142,7 +150,8 @@ class ClassStatsScorer:
             e0.record()
         bwd = items[0][1] is not None
         affine = items[0][2] is not None
-        ops.class_stats_grouped([i[0] for i in items], [i[4] for i in items], self.K, [i[5] for i in items], [i[6] for i in items],
+        # K + 1 classes for the kernel: label_keys maps every label outside [0, K) to the key K, which is row K here
+        ops.class_stats_grouped([i[0] for i in items], [i[4] for i in items], self.rows, [i[5] for i in items], [i[6] for i in items],
                                 dys=[i[1] for i in items] if bwd else None,
                                 scales=[i[2] for i in items] if affine else None, shifts=[i[3] for i in items] if affine else None,
                                 affine_mode=ops.AFFINE_INVSTD_MEAN if bwd else ops.AFFINE_SCALE_SHIFT)
@@ -292,10 +301,18 @@ class ClassStatsScorer:
         return {"eic": {n: self.eic[a:b].clone() for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}}
 
     def class_stats(self):
-        """Pass totals {name: (S1[K,C], S2[K,C])} plus per-resolution pixel counts {(h,w): cnt[K]}."""
+        """Pass totals {name: (S1[K,C], S2[K,C])} plus per-resolution pixel counts {(h,w): cnt[K]}; pixels outside
+        [0, K) (ignore label) are not in any class: their sums are `outside_stats()`."""
         src = self.totals if self.totals is not None else self.step_arena
-        views = {n: (src[0][:, a:b], src[1][:, a:b]) for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
+        K = self.K
+        views = {n: (src[0][:K, a:b], src[1][:K, a:b]) for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
         return views, {r: self.cnt[i] for i, r in enumerate(self.resolutions)}
+
+    def outside_stats(self):
+        """{name: (S1[C], S2[C])} of the pixels whose label is outside [0, K): class sums + these = sums over all pixels."""
+        src = self.totals if self.totals is not None else self.step_arena
+        K = self.K
+        return {n: (src[0][K, a:b], src[1][K, a:b]) for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])}
 
     def k1_time_ms(self):
         """(sum of K1 launch durations in ms, algorithmic bytes, launches) -- call after a synchronize."""
@@ -466,8 +483,11 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     if return_class_stats:
         totals = (sc.totals if sc.totals is not None else sc.step_arena).cpu()
         cnt = sc.cnt.cpu()
-        out["class_stats"] = {n: (totals[0][:, a:b].clone(), totals[1][:, a:b].clone())
+        K = sc.K  # rows [0, K): the classes; row K: pixels whose label is outside [0, K) (ignore label)
+        out["class_stats"] = {n: (totals[0][:K, a:b].clone(), totals[1][:K, a:b].clone())
                               for n, a, b in zip(sc.names, sc.offsets[:-1], sc.offsets[1:])}
+        out["outside_stats"] = {n: (totals[0][K, a:b].clone(), totals[1][K, a:b].clone())
+                                for n, a, b in zip(sc.names, sc.offsets[:-1], sc.offsets[1:])}
         out["class_counts"] = {r: cnt[i].clone() for i, r in enumerate(sc.resolutions)}
     torch.cuda.synchronize(device)
     out["_stats"] = dict(steps=len(plan), h2d_bytes=h2d, d2h_bytes=d2h, launches=ops.launch_count() - launches0,

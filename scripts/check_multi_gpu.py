@@ -68,7 +68,7 @@ if rank == 0:
     tot1 = sc.totals[0].cpu()
     name = sc.names[7]
     a, b = sc.offsets[7], sc.offsets[8]
-    ref = tot1[:, a:b]
+    ref = tot1[:K, a:b]  # class rows; row K holds the pixels outside [0, K)
     got = stats_dist[name][0]
     scale = ref.abs().mean()
     err = (got - ref).abs().max().item()

@@ -1,0 +1,124 @@
+"""BASELINE.json's configurations at their FULL sizes (ResNet-101 nets, 512x1024 / 512x512 images, K = 19 / 150 / 171,
+channels_last as benchmarked), checked through size-independent properties -- the oracle needs minutes per micro-batch
+at these sizes, so it is not run here:
+
+  * the rows of K1-bwd (K classes + the row of pixels outside [0, K): the synthetic labels contain ~3 % ignore
+    pixels) add up to autograd's own bn.weight.grad on every scored layer (the quantity pruners/dcfp_pruner.py:18
+    reads), and the EIC K2 derives from them is bit-exact given those gradients;
+  * per-resolution pixel counts equal a bincount of the nearest-down-sampled labels (exact);
+  * Cauchy-Schwarz per (class, channel): S1^2 <= cnt * S2;
+  * additivity over micro-batches: totals(A then B) == totals(A) + totals(B).
+
+Tolerances: sums of up to 2.6e5 fp32 terms in different orders (cuDNN's reduction vs K1's fp32-in-CTA / fp64-across-CTA),
+and cuDNN's backward is not bit-reproducible run to run: 1e-3 relative to the layer's mean magnitude."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import class_stats_ref, eic_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def ieee_fp32_convolutions():
+    """The additivity check compares runs: with tf32 convolutions cuDNN's choice of algorithm (it depends on the free
+    workspace) moves dy by ~1e-3 between two runs of the SAME micro-batch -- measured 0.2 % on a class's sum of squares --
+    which says nothing about the path under test.  IEEE fp32 convolutions keep the producer out of the comparison."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def _model(cfg):
+    from dcfp_b200.workloads.segnets import CONFIGS, build_segnet
+    c = CONFIGS[cfg]
+    model = build_segnet(c["arch"], c["backbone"], c["num_classes"], seed=0).to(DEV).to(memory_format=torch.channels_last)
+    return c, model
+
+
+def _batch(c, idx):
+    from dcfp_b200.workloads.synthetic import synthetic_batch
+    x, y = synthetic_batch(idx, c["num_classes"], c["height"], c["width"])
+    return x.to(DEV).contiguous(memory_format=torch.channels_last), y.to(DEV)
+
+
+def _totals(model, c, batches, mb, seed=0):
+    """`mb`: global micro-batch indices (they seed the Dropout2d masks: the same batch must keep the same index)."""
+    from dcfp_b200.scorer import CalibrationRun
+    run = CalibrationRun(model, c["num_classes"], r=0.999, seed=seed, keep_totals=True)
+    for i, (x, y) in zip(mb, batches):
+        run.step(x, y, mb_index=i)
+    sc = run.scorer
+    grads = [m.weight.grad.detach().double().cpu().numpy() for _, m in sc.layers]  # of the last step
+    out = dict(S=sc.totals.detach().cpu().numpy().copy(), cnt={r: v.cpu().numpy().copy() for r, v in sc.class_stats()[1].items()},
+               eic=sc.eic.cpu().numpy().copy(), gamma=sc.gamma().cpu().numpy().copy(), offsets=list(sc.offsets),
+               names=list(sc.names), grads=grads)
+    run.close()
+    return out
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3", "c4"])
+def test_full_size_properties(native, cfg):
+    c, model = _model(cfg)
+    K = c["num_classes"]
+    A, B = _batch(c, [0, 1]), _batch(c, [2, 3])
+    ta = _totals(model, c, [A], [0])
+    S1, S2 = ta["S"][0], ta["S"][1]  # [K + 1, sum C] fp64: the classes, then the pixels outside [0, K) (ignore label)
+    assert S1.shape == (K + 1, ta["offsets"][-1])
+
+    # class sums add up to autograd's gradient of every BN gamma
+    dgamma = S1.sum(0)
+    for name, a, b, g in zip(ta["names"], ta["offsets"][:-1], ta["offsets"][1:], ta["grads"]):
+        tol = 1e-3 * np.abs(g) + 1e-3 * np.abs(g).mean()
+        bad = np.abs(dgamma[a:b] - g) > tol
+        assert not bad.any(), "%s: %d / %d channels off, worst %.3g" % (name, bad.sum(), b - a, np.abs(dgamma[a:b] - g).max())
+    # EIC bit-exact given those gradients (first step: eic = flag * |g| * (1 - r))
+    exp = eic_ref.eic_step(0, dgamma.astype(np.float32), ta["gamma"], 0.999)
+    assert np.array_equal(ta["eic"].view(np.uint32), exp.view(np.uint32))
+
+    # counts: exact, per resolution
+    y = A[1].cpu()
+    assert (c["height"] // 8, c["width"] // 8) in ta["cnt"]
+    for (h, w), cnt in ta["cnt"].items():
+        lab = class_stats_ref.nearest_labels(y, h, w)
+        assert np.array_equal(cnt, np.bincount(lab[lab < K].reshape(-1).numpy(), minlength=K).astype(np.float64)), (h, w)
+        assert int(cnt.sum()) == int((lab < K).sum())
+
+    # Cauchy-Schwarz per (class, channel) at the resolution of each layer -- needs the layer's resolution: use the
+    # weakest form that needs no bookkeeping, cnt_max = the largest count of that class over all resolutions
+    def class_max(t):  # [K + 1, 1]: largest pixel count of each class over the resolutions; outside row: all pixels
+        m = np.max(np.stack(list(t["cnt"].values())), axis=0)
+        return np.concatenate([m, [2.0 * A[1].numel()]])[:, None]
+    cmax = class_max(ta)
+    assert (S1 * S1 <= cmax * S2 * (1 + 1e-4) + 1e-30).all()
+    assert (S2 >= 0).all()
+    empty = cmax[:, 0] == 0
+    assert (S1[empty] == 0).all() and (S2[empty] == 0).all()  # a class without pixels has no sums
+    assert np.abs(S1[K]).sum() > 0, "the synthetic labels contain ignored pixels: their row cannot be empty"
+
+    # additivity over micro-batches
+    tb = _totals(model, c, [B], [1])
+    tab = _totals(model, c, [A, B], [0, 1])
+    cmax_ab = class_max(tab)
+    for m in (0, 1):
+        want = ta["S"][m] + tb["S"][m]
+        got = tab["S"][m]
+        for a, b in zip(ta["offsets"][:-1], ta["offsets"][1:]):
+            s2 = ta["S"][1][:, a:b] + tb["S"][1][:, a:b]
+            # moment 0: signed sums cancel, so the error is bounded by the second-moment mass sqrt(cnt * S2), not by the
+            # entry itself; both moments get a floor at the layer's own scale: a class with a handful of pixels sums a
+            # few dy values that are themselves near-cancelling sums cuDNN does not reproduce bit for bit run to run
+            mass = np.sqrt(cmax_ab * s2) if m == 0 else s2
+            tol = 1e-3 * mass + 1e-4 * np.sqrt((mass * mass).mean()) + 1e-30
+            err = np.abs(got[:, a:b] - want[:, a:b])
+            if not (err <= tol).all():
+                k, col = np.unravel_index(np.argmax(err / tol), err.shape)
+                raise AssertionError("moment %d, columns %d:%d: %d entries off; worst at class %d column %d: got %.6g, want %.6g "
+                                     "(A %.6g + B %.6g), tol %.3g, class pixels <= %d, layer scale %.3g"
+                                     % (m, a, b, (err > tol).sum(), k, col, got[k, a + col], want[k, a + col], ta["S"][m][k, a + col],
+                                        tb["S"][m][k, a + col], tol[k, col], cmax_ab[k, 0], np.sqrt((mass * mass).mean())))
+    for r in ta["cnt"]:
+        assert np.array_equal(tab["cnt"][r], ta["cnt"][r] + tb["cnt"][r])
