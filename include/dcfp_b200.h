@@ -72,6 +72,10 @@ int dcfp_label_keys(const void* label, int label_dtype, int N, int H0, int W0, i
  *                           pruners/dcfp_pruner.py:18 reads as m.weight.grad)
  * class key:  keys[n][p] from dcfp_label_keys at this layer's (h, w); key >= K is dropped.
  *             keys == NULL puts every pixel in class 0 (K must be 1).
+ *             NOTE the identity above sums over ALL pixels: autograd's gradient includes the pixels
+ *             whose label is outside [0, K) (ignore label 255 -- no loss, but gradient below the
+ *             logits).  dcfp_label_keys gives them the key K; pass K + 1 here (K + 1 rows in S1/S2)
+ *             to collect them in a row of their own, as dcfp_b200/scorer.py does.
  * accumulates (+=, fp64):  S1[k*ld + c] += sum v,  S2[k*ld + c] += sum v*v
  */
 typedef struct dcfp_layer_desc {
