@@ -428,7 +428,7 @@ def run_b200_arm(args, c):
                            "l2": "per-step feature maps (%.1f GB read by K1) exceed the 126 MB L2; no explicit flush" % (k1_bytes / K / 1e9),
                            "layout": args.layout, "backward": "scores_only (no weight-gradient convolutions)" if args.scores_only else "full (all gradients, as the reference's training step)", "k1_flush_mib": args.flush_mb, "priming_steps": args.prime, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
                 "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "forward_functor": forward, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K,sumC] fp64 totals + counts at the end of the pass"}}
+                "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K+1,sumC] fp64 totals (K classes + the pixels outside [0,K)) + counts at the end of the pass"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
