@@ -405,3 +405,134 @@ def test_nchw_large_k_remap_overflow(native, K, dtype):
     _check(ops, x, label, K)
     dy = (torch.randn(N, C, h, w, generator=torch.Generator().manual_seed(K + 2)) * 1e-2).to(dtype)
     _check(ops, x, label, K, dy=dy, scale=torch.rand(C) + 0.5, shift=torch.randn(C))
+
+
+def _fuzz_cases(n_cases=160, seed=20240607):
+    """Seeded random shapes across every dispatch boundary of K1: channel counts around the 4 / 32 / 64 / 128 edges,
+    pixel counts around the TMA box sizes (ragged tails, planes shorter than one box, odd pixel counts under the
+    64-channel pixel-pair view), K around the slot-cache (12/13), table (24/25) and key (255) limits."""
+    import random
+    rnd = random.Random(seed)
+    Cs = [4, 8, 12, 28, 32, 36, 48, 60, 64, 68, 96, 124, 128, 132, 192, 256, 260, 320, 33, 7]
+    Ks = [1, 2, 11, 12, 13, 19, 23, 24, 25, 26, 60, 150, 171, 254, 255]
+    cases = []
+    for i in range(n_cases):
+        C = rnd.choice(Cs)
+        K = rnd.choice(Ks)
+        N = rnd.choice([1, 2, 3])
+        h = rnd.choice([1, 2, 3, 5, 8, 15, 16, 17, 31, 32, 33, 40, 64])
+        w = rnd.choice([1, 2, 4, 7, 8, 9, 16, 24, 31, 32, 33, 48, 65, 128])
+        layout = rnd.choice(["nchw", "nhwc"])
+        dtype = rnd.choice([torch.float32, torch.float32, torch.bfloat16])
+        functor = rnd.choice(["fwd", "fwd_affine", "bwd", "bwd"])
+        blob = rnd.random() < 0.7
+        cases.append((i, N, C, h, w, K, layout, dtype, functor, blob))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: "%d-%dx%dx%dx%d-K%d-%s-%s-%s" % (
+    c[0], c[1], c[2], c[3], c[4], c[5], c[6], "bf16" if c[7] == torch.bfloat16 else "f32", c[8]))
+def test_randomized_shapes_layouts_and_functors(native, case):
+    from dcfp_b200 import ops
+    i, N, C, h, w, K, layout, dtype, functor, blob = case
+    g = torch.Generator().manual_seed(1000 + i)
+    scale_up = [1, 2, 4, 8][i % 4]
+    H0, W0 = h * scale_up + (i % 3 if scale_up > 1 else 0), w * scale_up + (i % 2 if scale_up > 1 else 0)
+    label = _labels(N, H0, W0, K, [torch.uint8, torch.int32, torch.int64][i % 3], seed=2000 + i, blob=blob)
+    x = torch.randn(N, C, h, w, generator=g).to(dtype)
+    dy = scale = shift = None
+    if functor != "fwd":
+        scale = torch.rand(C, generator=g) + 0.5
+        shift = torch.randn(C, generator=g)
+    if functor == "bwd":
+        dy = (torch.randn(N, C, h, w, generator=g) * 0.1).to(dtype)
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+        if dy is not None:
+            dy = dy.contiguous(memory_format=torch.channels_last)
+    if dtype == torch.bfloat16:
+        # the oracle sees the SAME bf16-rounded inputs widened to fp32; tolerance stays the fp32-accumulation one
+        x32, dy32 = x.float(), None if dy is None else dy.float()
+    else:
+        x32, dy32 = x, dy
+    dev = torch.device("cuda")
+    S1 = torch.full((K, C + 3), 7.0, dtype=torch.float64, device=dev)  # guard columns: a shared-arena layout, ld = C + 3
+    S2 = torch.full_like(S1, 7.0)
+    S1[:, :C] = 0
+    S2[:, :C] = 0
+    cn = torch.zeros(K, dtype=torch.float64, device=dev)
+    keys = _keys(ops, label, h, w, K, cn)
+    to = lambda t: None if t is None else t.to(dev)
+    ops.class_stats(x.to(dev), keys, K, S1[:, :C], S2[:, :C], dy=to(dy), scale=to(scale), shift=to(shift))
+    torch.cuda.synchronize()
+    v = ref.functor_fwd(x32.float(), scale, shift) if dy is None else ref.functor_bwd(x32.float(), dy32.float(), scale, shift)
+    rc, r1, r2 = ref.class_stats(v, label, K)
+    mass = ref.abs_mass(v, label, K)
+    assert torch.equal(cn.cpu(), rc)
+    assert (S1[:, C:] == 7.0).all() and (S2[:, C:] == 7.0).all(), "wrote outside the layer's columns"
+    e1 = (S1[:, :C].cpu() - r1).abs()
+    assert (e1 <= RTOL * mass + 1e-30).all(), "S1 max rel-to-mass err %.3g" % (e1 / (mass + 1e-30)).max()
+    e2 = (S2[:, :C].cpu() - r2).abs()
+    assert (e2 <= RTOL * r2 + 1e-30).all(), "S2 max rel err %.3g" % (e2 / (r2 + 1e-30)).max()
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_randomized_grouped_launches_on_a_shared_arena(native, seed):
+    """What the scorer does: many layers of mixed shapes (and mixed layouts) in ONE grouped call, every layer owning a
+    column range of one [K, sum C] arena (row stride = sum C), backward functor with autograd-style (invstd, mean).
+    Checked per layer against the oracle, plus: nothing outside a layer's columns is touched."""
+    import random
+    from dcfp_b200 import ops
+    rnd = random.Random(900 + seed)
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3000 + seed)
+    K = rnd.choice([2, 12, 13, 19, 20, 25, 151, 172])
+    bwd = seed % 3 != 0
+    dtype = torch.bfloat16 if seed % 5 == 4 else torch.float32
+    N = rnd.choice([1, 2, 3])
+    res = [(rnd.choice([4, 8, 16, 17, 32]), rnd.choice([4, 8, 16, 24, 33, 64])) for _ in range(3)] + [(1, 1)]
+    label = _labels(N, 128, 192, K, torch.uint8, seed=4000 + seed, blob=seed % 2 == 0)
+    layers = []
+    for _ in range(rnd.randint(3, 14)):
+        C = rnd.choice([4, 48, 64, 64, 96, 128, 128, 256, 320, 512, 36, 6])
+        h, w = rnd.choice(res)
+        nhwc = rnd.random() < 0.6
+        layers.append((C, h, w, nhwc))
+    total = sum(l[0] for l in layers) + 5
+    A1 = torch.full((K, total), 3.0, dtype=torch.float64, device=dev)
+    A2 = torch.full_like(A1, 3.0)
+    keys = {}
+    xs, dys, scs, shs, kl, S1s, S2s, refs = [], [], [], [], [], [], [], []
+    pos = 2  # two guard columns in front, three behind
+    for C, h, w, nhwc in layers:
+        fmt = torch.channels_last if nhwc else torch.contiguous_format
+        x = (torch.randn(N, C, h, w, generator=g) * 1.5 + 0.2).to(dtype).contiguous(memory_format=fmt)
+        dy = (torch.randn(N, C, h, w, generator=g) * 0.05).to(dtype).contiguous(memory_format=fmt) if bwd else None
+        mean = torch.randn(C, generator=g) * 0.3
+        invstd = torch.rand(C, generator=g) + 0.5
+        if (h, w) not in keys:
+            keys[(h, w)] = _keys(ops, label, h, w, K)
+        A1[:, pos:pos + C] = 0
+        A2[:, pos:pos + C] = 0
+        xs.append(x.to(dev)); dys.append(None if dy is None else dy.to(dev)); scs.append(invstd.to(dev)); shs.append(mean.to(dev))
+        kl.append(keys[(h, w)]); S1s.append(A1[:, pos:pos + C]); S2s.append(A2[:, pos:pos + C])
+        if bwd:
+            v = ref.functor_bwd(x.float(), dy.float(), invstd, -mean * invstd)
+        else:
+            v = ref.functor_fwd(x.float(), invstd, -mean * invstd)
+        refs.append((pos, C, v))
+        pos += C
+    # layers of one call must share dtype and functor; layouts may mix
+    ops.class_stats_grouped(xs, kl, K, S1s, S2s, dys=dys if bwd else None, scales=scs, shifts=shs, affine_mode=ops.AFFINE_INVSTD_MEAN)
+    torch.cuda.synchronize()
+    own = torch.zeros(total, dtype=torch.bool)
+    for p, C, v in refs:
+        own[p:p + C] = True
+        _, r1, r2 = ref.class_stats(v, label, K)
+        mass = ref.abs_mass(v, label, K)
+        e1 = (A1[:, p:p + C].cpu() - r1).abs()
+        # (x - mean) * invstd evaluated as fma(x, invstd, -mean * invstd): one extra rounding of the shift
+        assert (e1 <= 2 * RTOL * mass + 1e-30).all(), "columns %d:%d S1 max rel-to-mass err %.3g" % (p, p + C, (e1 / (mass + 1e-30)).max())
+        e2 = (A2[:, p:p + C].cpu() - r2).abs()
+        assert (e2 <= 4 * RTOL * r2 + 1e-30).all(), "columns %d:%d S2 max rel err %.3g" % (p, p + C, (e2 / (r2 + 1e-30)).max())
+    assert (A1.cpu()[:, ~own] == 3.0).all() and (A2.cpu()[:, ~own] == 3.0).all(), "wrote outside the layers' columns"
