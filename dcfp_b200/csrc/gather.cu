@@ -110,7 +110,9 @@ int validate_gather(const dcfp_gather_desc& d, int idx) {
   DCFP_REQUIRE(d.n_out >= 0 && d.n_in >= 0 && d.I > 0 && d.khw > 0, DCFP_EINVAL, "channel_gather[%d]: bad extents", idx);
   const bool empty = d.n_out == 0 || d.n_in == 0;
   DCFP_REQUIRE(empty || (d.src && d.dst), DCFP_EINVAL, "channel_gather[%d]: null src/dst", idx);
-  DCFP_REQUIRE(d.in_idx != nullptr || d.n_in == d.I, DCFP_EINVAL, "channel_gather[%d]: in_idx NULL requires n_in == I", idx);
+  // an EMPTY selection arrives as a zero-length index list, whose device pointer may legitimately be NULL
+  DCFP_REQUIRE(d.in_idx != nullptr || d.n_in == d.I || d.n_in == 0, DCFP_EINVAL,
+               "channel_gather[%d]: in_idx NULL requires n_in == I", idx);
   DCFP_REQUIRE(static_cast<long long>(d.n_in) * d.khw < (1LL << 31) - kGatherTile, DCFP_ETOOBIG,
                "channel_gather[%d]: output row too long", idx);
   return 0;

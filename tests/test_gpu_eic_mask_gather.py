@@ -179,3 +179,72 @@ def test_thresholds_large_score_vector_takes_the_layer_walk(native):
         assert [float(t) for t in thresh] == [float(t) for t in t_ref]
         m_ref = np.concatenate(mask_ref.masks(scores, groups, t_ref, 0.02))
         assert np.array_equal(mask, m_ref)
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_randomized_thresholds_masks_and_gathers_bit_exact(native, seed):
+    """Seeded random layer tables (1..40 layers of 1..2048 channels, either group possibly empty), score distributions
+    with heavy ties, global_percent from 0 to 0.999, layer_keep from 0 to 1 -- and
+    random weight shapes / index lists (empty, single, all) through both gather entry points.  All bit-exact."""
+    from dcfp_b200 import ops
+    rng = np.random.RandomState(7000 + seed)
+    n_layers = int(rng.randint(1, 41))
+    sizes = [int(rng.choice([1, 2, 3, 7, 16, 33, 48, 64, 128, 255, 256, 512, 1024, 2048])) for _ in range(n_layers)]
+    mode = seed % 4
+    groups = [int(rng.randint(0, 2)) for _ in sizes] if mode != 3 else [1] * n_layers
+    kind = rng.randint(0, 4)
+    scores = []
+    for c in sizes:
+        if kind == 0:
+            s = rng.rand(c)
+        elif kind == 1:
+            s = np.abs(rng.standard_normal(c)) ** 3 * 1e-7
+        elif kind == 2:  # few distinct values: ties everywhere, including at the threshold
+            s = rng.randint(0, 4, c) * 0.25
+        else:
+            s = rng.rand(c) * (rng.rand(c) > 0.6)
+        scores.append(s.astype(np.float32))
+    gp = float(rng.choice([0.0, 0.01, 0.3, 0.5, 0.52, 0.7, 0.9, 0.98, 0.999]))
+    layer_keep = float(rng.choice([0.0, 0.01, 0.02, 0.1, 0.5, 1.0]))
+    mask, thresh, kept = _run_mask(ops, scores, groups, gp, layer_keep)
+    t_ref = mask_ref.thresholds(scores, groups, gp)
+    m_ref = np.concatenate(mask_ref.masks(scores, groups, t_ref, layer_keep))
+    for g in (0, 1):
+        if any(gg == g for gg in groups):
+            assert np.float32(thresh[g]) == np.float32(t_ref[g]), (g, gp)
+    assert np.array_equal(mask, m_ref), (gp, layer_keep)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    assert np.array_equal(kept, [int(m_ref[a:b].sum()) for a, b in zip(offs[:-1], offs[1:])])
+
+    # gathers: conv weights [O, I, kh, kw], BN vectors [O], depth-1 kernels, bf16-sized elements via float16 views
+    srcs, ois, iis, exp = [], [], [], []
+    for _ in range(int(rng.randint(1, 12))):
+        O = int(rng.choice([1, 3, 19, 48, 64, 150, 256, 513]))
+        if rng.rand() < 0.3:
+            shape = (O,)
+        else:
+            khw = [(1, 1), (3, 3), (1, 7), (7, 7)][int(rng.randint(0, 4))]
+            shape = (O, int(rng.choice([1, 3, 16, 64, 255, 320]))) + khw
+        W = rng.standard_normal(shape).astype(np.float32)
+
+        def pick(n):
+            r = rng.rand()
+            if r < 0.15:
+                return None
+            if r < 0.25:
+                return np.arange(n, dtype=np.int32)
+            if r < 0.35:
+                return np.array([int(rng.randint(0, n))], dtype=np.int32)
+            return np.nonzero(rng.rand(n) > rng.rand())[0].astype(np.int32)
+        o = pick(shape[0])
+        i = pick(shape[1]) if len(shape) > 1 else None
+        srcs.append(torch.from_numpy(W).to(DEV))
+        ois.append(None if o is None else torch.from_numpy(o).to(DEV))
+        iis.append(None if i is None else torch.from_numpy(i).to(DEV))
+        exp.append(gather_ref.gather(W, o, i))
+    outs = ops.channel_gather_grouped(srcs, ois, iis)
+    for got, e, s, o, i in zip(outs, exp, srcs, ois, iis):
+        assert tuple(got.shape) == e.shape and np.array_equal(got.cpu().numpy().view(np.uint32), e.view(np.uint32))
+        if o is not None or i is not None:
+            one = ops.channel_gather(s, o, i)
+            assert tuple(one.shape) == e.shape and np.array_equal(one.cpu().numpy().view(np.uint32), e.view(np.uint32))
