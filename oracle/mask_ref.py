@@ -9,7 +9,7 @@ Follows pruners/dcfp_pruner.py:43-66 (get_thresh) and :68-92 (gen_channel_mask):
     min_keep highest-scoring channels are switched on as well.  The reference takes them from an
     unstable torch.sort(descending=True), so ties that straddle the cut are implementation-defined;
     this restatement (and the CUDA kernel) break them lowest-index-first.
-Pinned against the unmodified reference by tests/golden/sweep_c{1,3}.npz and prune_c{1..4}.npz.
+Pinned against the unmodified reference by tests/golden/sweep_c{1..4}.npz and prune_c{1..4}.npz.
 """
 import numpy as np
 

@@ -15,7 +15,7 @@ CUDA path on the GPU box, where /root/reference does not exist.
                        SHA-256 of every tensor of the pruned state_dict
   prune_c1_beta.npz    same with non-zero BN beta -> exercises bias compensation (channel_pruner.py:873-905);
                        stores the compensated running_mean vectors (fp32 GEMV: compared with a tolerance)
-  sweep_c{1,3}.npz     thresholds + raw keep masks for all 25 global_percent values prune.py can visit
+  sweep_c{1..4}.npz    thresholds + raw keep masks for all 25 global_percent values prune.py can visit
   balance.npz          BaseDataSet.get_label (datasets/Base.py:73-89): class-balance pixel weights, modes 1 and 2
   scoring_small.npz    reference Seg_Model + CriterionDSN + dcfp_pruning over 2 steps on 2x3x64x128 inputs:
                        per-step BN-gamma gradients and the final EIC (pins oracle/scoring_ref.py)
@@ -228,13 +228,15 @@ def gen_prune(only_beta=False):
     print("wrote prune_c1_beta.npz; running_mean tensors:", len(moved), "of base", sum(k.endswith("running_mean") for k in base))
 
 
-def gen_sweep():
+def gen_sweep(only=None):
     """get_thresh + gen_channel_mask (pruners/dcfp_pruner.py:43-92) for EVERY global_percent prune.py can visit
     (0.5, 0.52, ... accumulated in floating point exactly as prune.py:91,122 does), eic-like scores with 40 % exact
     zeros: thresholds (bits) and the raw per-link masks before propagation."""
     ref = ref_compat.load_reference()
     tmp = "/tmp/_golden_score.pth"
-    for cfg_name, seed in (("c1", 11), ("c3", 12)):
+    for cfg_name, seed in (("c1", 11), ("c3", 12), ("c2", 13), ("c4", 14)):
+        if only and cfg_name not in only:
+            continue
         model = build_ref_model(ref, cfg_name)
         eic = make_scores(model, "eic_like", seed)
         torch.save({"eic": {k: torch.from_numpy(v) for k, v in eic.items()}}, tmp)
@@ -338,6 +340,6 @@ if __name__ == "__main__":
     if "balance" in what:
         gen_balance()
     if "sweep" in what:
-        gen_sweep()
+        gen_sweep([w for w in what if w in ("c1", "c2", "c3", "c4")])  # e.g. `make_golden.py sweep c2 c4`
     if "prune" in what or "beta" in what:
         gen_prune(only_beta="prune" not in what)

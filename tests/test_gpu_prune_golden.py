@@ -62,7 +62,7 @@ def test_pruned_model_runs(native):
     assert kept < raw
 
 
-@pytest.mark.parametrize("cfg", ["c1", "c3"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4"])
 def test_global_percent_sweep_bit_exact(native, cfg):
     """K2 (radix-select thresholds, strict-> masks, min-keep fallback) for all 25 global_percent values prune.py can
     visit, eic-like scores with 40 % exact zeros: thresholds and masks bit-exact vs the unmodified reference."""

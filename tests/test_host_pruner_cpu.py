@@ -90,7 +90,7 @@ def test_random_pruner_and_min_keep():
     assert out[0].shape == (1, 19, 64, 64)
 
 
-@pytest.mark.parametrize("cfg", ["c1", "c3"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4"])
 def test_global_percent_sweep_matches_reference_golden(cfg):
     """oracle backend: pins oracle/mask_ref.py and the host bookkeeping of DCFPPruner._select for every percent."""
     with oracle_backend():
