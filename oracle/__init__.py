@@ -14,7 +14,7 @@ Pinning status (details in DESIGN.md section "Oracle"):
   tests / golden vectors, so these restatements are pinned against outputs of the
   *unmodified reference code executed in the build container* (``oracle/ref_compat.py``
   + ``tests/golden/make_golden.py``; fixtures are committed under ``tests/golden/``:
-  ``eic_steps.npz``, ``prune_c{1..4}.npz``, ``prune_c1_beta.npz``, ``sweep_c{1,3}.npz``,
+  ``eic_steps.npz``, ``prune_c{1..4}.npz``, ``prune_c1_beta.npz``, ``sweep_c{1..4}.npz``,
   ``scoring_small.npz``).
 * ``class_stats_ref`` (``bwd`` value functor): pinned through the identity
   ``sum_k S1[k, c] == bn.weight.grad`` of the reference's autograd path.
