@@ -121,3 +121,31 @@ def test_class_balance_restatement_matches_reference_bits():
         exp = z["weight_%d_%d" % (c["case"], c["img"])]
         assert w.dtype == np.float64 and np.array_equal(w.view(np.uint64), exp.view(np.uint64)), c
         assert cnt.sum() == (label != 255).sum()
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_factored_batchnorm_equals_autograd(relu):
+    """oracle/bn_ref.py (the sum-factored BN (+ReLU) forward/backward a fused BN + K1 kernel pair computes)
+    against torch autograd of nn.BatchNorm2d -> nn.ReLU in fp64, including the running-statistics update."""
+    from oracle import bn_ref
+    torch.manual_seed(3)
+    N, C, h, w = 3, 11, 7, 5
+    x = (torch.randn(N, C, h, w, dtype=torch.float64) * 2 + 0.5).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).double().train()
+    with torch.no_grad():
+        bn.weight.uniform_(-1.5, 1.5)  # negative gammas flip the gate's direction
+        bn.bias.normal_()
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    y = bn(x)
+    y = torch.relu(y) if relu else y
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr, mean, invstd = bn_ref.bn_relu_forward(x.detach(), bn.weight.detach(), bn.bias.detach(), bn.eps, relu=relu)
+    assert torch.allclose(yr, y.detach(), rtol=1e-12, atol=1e-12)
+    dx, dg, db = bn_ref.bn_relu_backward(x.detach(), dy, bn.weight.detach(), bn.bias.detach(), mean, invstd, relu=relu)
+    assert torch.allclose(dx, x.grad, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(dg, bn.weight.grad, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(db, bn.bias.grad, rtol=1e-10, atol=1e-12)
+    n = N * h * w
+    rm, rv = bn_ref.running_stats_update(rm0, rv0, mean, 1.0 / (invstd * invstd) - bn.eps, n, bn.momentum)
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-12, atol=1e-12) and torch.allclose(rv, bn.running_var, rtol=1e-10, atol=1e-12)
