@@ -73,3 +73,16 @@ def class_stats_bwd(x, dy, mean, invstd, label, K):
 def abs_mass(v, label, K):
     """sum |v| per (class, channel): the scale against which fp32-accumulation error is judged."""
     return class_stats(torch.as_tensor(v).double().abs(), label, K)[1]
+
+
+def outside_stats(v, label, K):
+    """(S1[C], S2[C]) over the pixels whose nearest-down-sampled label is OUTSIDE [0, K) -- the ignore label.  Those
+    pixels carry no loss (criterion.py:52-60, ignore_index) but they do carry gradient at every layer below the logits,
+    and autograd's bn.weight.grad sums over them: sum_k S1[k] + outside S1 == dgamma, not sum_k S1[k] alone.  The
+    scorer keeps them in row K of its arenas (dcfp_b200/scorer.py)."""
+    v = torch.as_tensor(v).double()
+    n, c, h, w = v.shape
+    lab = nearest_labels(label, h, w).reshape(-1)
+    flat = v.permute(0, 2, 3, 1).reshape(-1, c)
+    out = flat[(lab < 0) | (lab >= K)]
+    return out.sum(0), (out * out).sum(0)

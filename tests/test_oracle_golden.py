@@ -149,3 +149,31 @@ def test_factored_batchnorm_equals_autograd(relu):
     n = N * h * w
     rm, rv = bn_ref.running_stats_update(rm0, rv0, mean, 1.0 / (invstd * invstd) - bn.eps, n, bn.momentum)
     assert torch.allclose(rm, bn.running_mean, rtol=1e-12, atol=1e-12) and torch.allclose(rv, bn.running_var, rtol=1e-10, atol=1e-12)
+
+
+def test_class_rows_plus_outside_row_equal_autograd_dgamma():
+    """The identity the scorer's EIC feed rests on, with the ignore label present: the K class rows of the backward
+    functor do NOT add up to bn.weight.grad -- the pixels labelled 255 carry gradient too (they only carry no loss).
+    Class rows + the outside row do.  (A product bug of exactly this kind passed every all-valid-label test.)"""
+    torch.manual_seed(5)
+    N, C, h, w, K = 2, 6, 12, 16, 5
+    x = (torch.randn(N, C, h, w, dtype=torch.float64) * 1.5 + 0.3).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).double().train()
+    head = torch.nn.Conv2d(C, K, 3, padding=1).double()  # a receptive field: ignored pixels get gradient from neighbours
+    label = torch.randint(0, K, (N, 4 * h, 4 * w))
+    label[:, 10:30, 5:40] = 255
+    y = bn(x)
+    logits = F.interpolate(head(torch.relu(y)), size=label.shape[1:], mode="bilinear", align_corners=True)
+    y.retain_grad()
+    F.cross_entropy(logits, label, ignore_index=255).backward()
+    xd = x.detach()
+    mean = xd.mean(dim=(0, 2, 3))
+    invstd = torch.rsqrt(xd.var(dim=(0, 2, 3), unbiased=False) + bn.eps)
+    v = class_stats_ref.functor_bwd(xd, y.grad, invstd, -mean * invstd)
+    cnt, S1, S2 = class_stats_ref.class_stats(v, label, K)
+    o1, o2 = class_stats_ref.outside_stats(v, label, K)
+    g = bn.weight.grad
+    assert cnt.sum() < N * h * w and float(o2.sum()) > 0  # some pixels are outside, and they do carry gradient
+    assert torch.allclose(S1.sum(0) + o1, g, rtol=1e-9, atol=1e-12)
+    assert not torch.allclose(S1.sum(0), g, rtol=1e-3, atol=1e-9), "the class rows alone must NOT reproduce dgamma here"
+    assert torch.allclose(S2.sum(0) + o2, (v * v).sum(dim=(0, 2, 3)), rtol=1e-12)
