@@ -10,8 +10,6 @@ GFLOPs strings, same outputs.
 """
 import copy
 
-import torch
-
 from . import flops as _flops
 from .channel_pruner import _structural_clone, init_pruned_model
 from .dcfp_pruner import DCFPPruner

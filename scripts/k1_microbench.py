@@ -1,5 +1,6 @@
 """Quick K1 timing on resident feature maps (development aid; bench.py is the judged entry)."""
-import sys, os, time
+import os
+import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dcfp_b200 import ops
