@@ -62,6 +62,9 @@ def parse_args():
     p.add_argument("--scores-only", action="store_true",
                    help="freeze every non-BN parameter during scoring: no weight-gradient convolutions (the scores do not "
                         "need them); default off = the reference's full backward")
+    p.add_argument("--no-fused", action="store_true",
+                   help="score with torch/cuDNN BatchNorm + ReLU and the hook-fed, deferred K1 launches (round 1's path) instead of "
+                        "the fused BN(+ReLU) kernels whose backward yields the class-keyed sums (SURVEY 8 f1)")
     p.add_argument("--no-forward-functor", action="store_true",
                    help="skip the extra forward-only region (north_star-literal statistics: K1 with v = BN output)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,7 +267,7 @@ def run_b200_arm(args, c):
 
     # ---- phase A: inputs resident in HBM -------------------------------------------------------------------
     run = CalibrationRun(model, c["num_classes"], r=0.999, flush_bytes=args.flush_mb << 20, keep_totals=True, timing=True, seed=0,
-                         scores_only=args.scores_only)
+                         scores_only=args.scores_only, fused=not args.no_fused)
     sc = run.scorer
     # nvidia-smi attaches to the driver when it starts (stalls launches for ~0.2 s): start it before the set-up steps
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
@@ -284,6 +287,7 @@ def run_b200_arm(args, c):
         run.step(*resident[s], mb_index=s * world + rank)
     barrier()
     sc.k1_events.clear()
+    sc.phase_events.clear()
     launches0 = ops.launch_count()
     mem0 = torch.cuda.memory_stats(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,7 +321,17 @@ def run_b200_arm(args, c):
              "alloc_retries_in_timed_region": mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0),
              "debug": dbg, "reserved_gb": mem1.get("reserved_bytes.all.current", 0) / 1e9, "allocated_peak_gb": mem1.get("allocated_bytes.all.peak", 0) / 1e9}
     k1_ms, k1_bytes, k1_launches = sc.k1_time_ms()
-    share_a = k1_ms / max(e0.elapsed_time(e1), 1e-9)
+    region_ms = max(e0.elapsed_time(e1), 1e-9)
+    phases = {k: {"ms_per_step": ms / K, "algorithmic_gb_per_step": nb / K / 1e9, "calls_per_step": n / K,
+                  "achieved_gbs": (nb / (ms * 1e-3) / 1e9) if ms > 0 else None, "share_of_step": ms / region_ms}
+              for k, (ms, nb, n) in sc.phase_times().items()}
+    fused_on = "bn_bwd_reduce" in phases
+    if k1_launches:
+        phases["k1_deferred"] = {"ms_per_step": k1_ms / K, "algorithmic_gb_per_step": k1_bytes / K / 1e9, "calls_per_step": k1_launches / K,
+                                 "achieved_gbs": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None, "share_of_step": k1_ms / region_ms}
+    if fused_on:  # the dominant kernel of the path is now B1: the class-keyed reduction inside the fused BN backward
+        k1_ms, k1_bytes, k1_launches = sc.phase_times()["bn_bwd_reduce"]
+    share_a = k1_ms / region_ms
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     sc.all_reduce_totals()  # the single end-of-pass statistics all-reduce (outside the per-step timing, reported below)
     if world > 1:
@@ -376,13 +390,13 @@ def run_b200_arm(args, c):
         if W:
             xw, yw = global_order(0, W)
             score_calibration_set(model, xw, yw, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20,
-                                  scores_only=args.scores_only)
+                                  scores_only=args.scores_only, fused=not args.no_fused)
         xk, yk = global_order(W, W + K)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = score_calibration_set(model, xk, yk, c["num_classes"], micro_batch=mb, flush_bytes=args.flush_mb << 20,
-                                    scores_only=args.scores_only)
+                                    scores_only=args.scores_only, fused=not args.no_fused)
         e1.record()
         barrier()
         ms_b = max_over_ranks(e0.elapsed_time(e1))
@@ -400,7 +414,9 @@ def run_b200_arm(args, c):
             traffic = json.load(f)
     except Exception:
         pass
-    roofline = {"kernel": "dcfp::%s<float, BWD> (K1, label-keyed segmented reduction, v = dy * xhat)" %
+    roofline = {"kernel": ("dcfp::class_stats_nhwc_kernel<float, BWD, FUSED> (B1 of the fused BN backward: label-keyed segmented reduction "
+                           "of v = dz * xhat with the ReLU gate recomputed, + sum dz, sum v; one launch per BN layer)") if fused_on else
+                          "dcfp::%s<float, BWD> (K1, label-keyed segmented reduction, v = dy * xhat)" %
                           ("class_stats_nhwc_kernel" if nhwc else "class_stats_kernel"),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
@@ -425,9 +441,11 @@ def run_b200_arm(args, c):
                                          if tf32 else "fp32 (cudnn.allow_tf32=False)") + "; K1/K2/K3 arithmetic is fp32 (fp64 across CTAs)",
                            "protocol": "zero_grad -> loss(x, y, deepsup) -> backward [K1 on every scored BN: S[k,c] += dy*xhat] -> "
                                        "fold -> all-reduce(dgamma)/N -> EIC update; no optimizer step",
+                           "bn": ("fused: dcfp BN(+ReLU) forward / backward kernels, class-keyed sums inside the BN backward" if fused_on else
+                                  "torch/cuDNN BatchNorm + ReLU, hook-fed deferred K1"),
                            "l2": "per-step feature maps (%.1f GB read by K1) exceed the 126 MB L2; no explicit flush" % (k1_bytes / K / 1e9),
                            "layout": args.layout, "backward": "scores_only (no weight-gradient convolutions)" if args.scores_only else "full (all gradients, as the reference's training step)", "k1_flush_mib": args.flush_mb, "priming_steps": args.prime, "parallelism": "dp%d (micro-batches dealt round-robin)" % world},
-                "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "forward_functor": forward, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "step_ms": step_ms, "allocator": alloc, "roofline": roofline, "path_phases": phases, "forward_functor": forward, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "stats_allreduce": {"bytes": arena_bytes, "ms": allreduce_ms, "what": "one all-reduce of the [2,K+1,sumC] fp64 totals (K classes + the pixels outside [0,K)) + counts at the end of the pass"}}
         print(json.dumps(line), flush=True)
     if world > 1:

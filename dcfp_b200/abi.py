@@ -22,7 +22,15 @@ class LayerDesc(ctypes.Structure):
                 ("keys", ctypes.c_void_p), ("S1", ctypes.c_void_p), ("S2", ctypes.c_void_p),
                 ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
                 ("K", ctypes.c_int32), ("dtype", ctypes.c_int32), ("layout", ctypes.c_int32), ("ld", ctypes.c_int32),
-                ("affine_mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("affine_mode", ctypes.c_int32), ("hints", ctypes.c_int32)]
+
+
+class BnDesc(ctypes.Structure):
+    """struct dcfp_bn_desc"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("x", "y", "dy", "dx", "gamma", "beta", "mean", "invstd", "running_mean", "running_var",
+                                               "scratch", "keys", "S1", "S2", "dgamma", "dbeta")] + \
+               [(n, ctypes.c_int32) for n in ("N", "C", "h", "w", "dtype", "relu", "K", "ld")] + \
+               [("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("phases", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class GatherDesc(ctypes.Structure):
@@ -56,6 +64,11 @@ def load(path=LIB_PATH):
     lib.dcfp_label_keys.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.dcfp_class_stats.argtypes = [ctypes.POINTER(LayerDesc), vp]
     lib.dcfp_class_stats_grouped.argtypes = [ctypes.POINTER(LayerDesc), i32, vp]
+    lib.dcfp_bn_supported.argtypes = [i32, i32, i32, i32, i32]
+    lib.dcfp_bn_scratch_bytes.restype = ctypes.c_size_t
+    lib.dcfp_bn_scratch_bytes.argtypes = [i32]
+    lib.dcfp_bn_forward.argtypes = [ctypes.POINTER(BnDesc), vp]
+    lib.dcfp_bn_backward.argtypes = [ctypes.POINTER(BnDesc), vp]
     lib.dcfp_eic_update.argtypes = [vp, vp, vp, i32, vp, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_eic_update_flat.argtypes = [vp, vp, vp, i32, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_reduce_classes.argtypes = [vp, i32, i32, vp, vp]

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 ABI_LIB = os.path.join(LIBDIR, "libdcfp_b200.so")
 OPS_LIB = os.path.join(LIBDIR, "dcfp_torch_ops.so")
 
-CU_SOURCES = ["class_stats.cu", "eic_select.cu", "gather.cu", "balance.cu", "abi.cu"]
+CU_SOURCES = ["class_stats.cu", "bn_fused.cu", "eic_select.cu", "gather.cu", "balance.cu", "abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-extended-lambda",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

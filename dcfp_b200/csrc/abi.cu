@@ -39,6 +39,17 @@ int finish_launch(const char* what) {
   return 0;
 }
 
+int num_sms() {
+  static std::atomic<int> cached[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return kNumSMs;
+  int v = cached[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+  cached[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
 int ensure_smem(const void* func, int bytes) {
   if (bytes <= 48 * 1024) return 0;
   int dev = 0;

@@ -93,7 +93,7 @@ extern "C" int dcfp_class_balance_weights(const void* label, int label_dtype, in
   const long long hw = static_cast<long long>(H) * W;
   cudaError_t e = cudaMemsetAsync(class_num, 0, static_cast<size_t>(N) * (K + 1) * sizeof(int64_t), s);
   if (e != cudaSuccess) return cuda_fail(e, "class_balance_weights: memset");
-  const int chunks = static_cast<int>(std::min<long long>((hw + 4095) / 4096, 2LL * kNumSMs));
+  const int chunks = static_cast<int>(std::min<long long>((hw + 4095) / 4096, 2LL * num_sms()));
   dim3 grid(chunks, N);
   image_hist_kernel<<<grid, 256, 0, s>>>(label, label_dtype, hw, K, ignore_label, reinterpret_cast<long long*>(class_num));
   int rc = finish_launch("image_hist");

@@ -1,0 +1,113 @@
+// Fused BN: scratch layout shared by the reduction kernels (bn_stats_kernel, the FUSED instantiation of K1) and the
+// element-wise kernels (bn_apply_kernel, bn_dx_kernel), and the "last CTA finalises" step between them.
+//
+// Same-address fp64 atomics serialise in the L2 slice at ~38 cycles each (measured: a per-layer K1 launch whose 1 184
+// warps each added their rows to the same 2*C addresses spent 20-60 us in that tail).  So per-channel totals go to one of
+// kBnStripes copies (stripe = blockIdx % kBnStripes), after a CTA-level combine, and the LAST CTA of the reduction kernel
+// (ticket counter) sums the stripes once, does the fp64 arithmetic once per channel and leaves five fp32 coefficient
+// vectors for the element-wise pass -- whose 500+ blocks then start with eight coalesced loads instead of fp64 math.
+#pragma once
+#include "common.cuh"
+
+namespace dcfp {
+
+constexpr int kBnStripes = 8;
+
+// scratch = double stripes[kBnStripes][2][C] | float coef[5][C] | unsigned counter (+ pad); ZERO on entry
+__host__ __device__ inline size_t bn_scratch_bytes(int C) {
+  return static_cast<size_t>(kBnStripes) * 2 * C * sizeof(double) + static_cast<size_t>(5) * C * sizeof(float) + 16;
+}
+__host__ __device__ inline double* bn_stripes(void* scratch) { return static_cast<double*>(scratch); }
+__host__ __device__ inline float* bn_coef(void* scratch, int C) {
+  return reinterpret_cast<float*>(static_cast<char*>(scratch) + static_cast<size_t>(kBnStripes) * 2 * C * sizeof(double));
+}
+__host__ __device__ inline unsigned* bn_counter(void* scratch, int C) { return reinterpret_cast<unsigned*>(bn_coef(scratch, C) + 5 * C); }
+
+struct BnFinal {
+  void* scratch;
+  const float* gamma;
+  const float* beta;
+  float* mean;          // forward: out;  backward: in
+  float* invstd;
+  float* running_mean;  // forward, optional
+  float* running_var;
+  float* dgamma;        // backward out
+  float* dbeta;
+  double inv_m;         // 1 / (N*h*w)
+  double unbias;        // M / (M - 1)
+  float eps, momentum;
+  int C;
+};
+
+// true in exactly one CTA per launch: the one that arrives last.  Must be called by ALL threads of every CTA after
+// their global atomics; resets the counter for the next launch that reuses the scratch.
+__device__ __forceinline__ bool bn_last_cta(unsigned* counter) {
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  const bool last = s_ticket == gridDim.x * gridDim.y - 1;
+  if (last) {
+    __threadfence();
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+  return last;
+}
+
+__device__ __forceinline__ void bn_sum_stripes(const double* stripes, int C, int c, double& s0, double& s1) {
+  s0 = s1 = 0.0;
+#pragma unroll
+  for (int s = 0; s < kBnStripes; ++s) {
+    s0 += __ldcg(stripes + static_cast<size_t>(s) * 2 * C + c);
+    s1 += __ldcg(stripes + static_cast<size_t>(s) * 2 * C + C + c);
+  }
+}
+
+// forward: stripes hold (sum x, sum x^2).  coef[0] = scale = gamma * invstd, coef[1] = shift = fma(-mean, scale, beta):
+// the backward re-evaluates these two fp32 expressions from the saved mean / invstd, so the ReLU gate is bit-exact.
+__device__ __forceinline__ void bn_finalize_forward(const BnFinal& F) {
+  float* coef = bn_coef(F.scratch, F.C);
+  const double* stripes = bn_stripes(F.scratch);
+  for (int c = threadIdx.x; c < F.C; c += blockDim.x) {
+    double s, q;
+    bn_sum_stripes(stripes, F.C, c, s, q);
+    const double mean = s * F.inv_m;
+    const double var = fmax(q * F.inv_m - mean * mean, 0.0);
+    const float mean_f = static_cast<float>(mean);
+    const float invstd_f = static_cast<float>(rsqrt(var + static_cast<double>(F.eps)));
+    const float scale = __fmul_rn(F.gamma[c], invstd_f);
+    coef[c] = scale;
+    coef[F.C + c] = __fmaf_rn(-mean_f, scale, F.beta[c]);
+    F.mean[c] = mean_f;
+    F.invstd[c] = invstd_f;
+    if (F.running_mean != nullptr) {
+      F.running_mean[c] = static_cast<float>((1.0 - F.momentum) * F.running_mean[c] + F.momentum * mean);
+      F.running_var[c] = static_cast<float>((1.0 - F.momentum) * F.running_var[c] + F.momentum * var * F.unbias);
+    }
+  }
+}
+
+// backward: stripes hold (sum dz, sum dz * xhat).  dx = a * dz + b * x + d with a = gamma * invstd,
+// b = -a * invstd * dgamma / M, d = a * (mean * invstd * dgamma / M - dbeta / M);  coef = [a, b, d, zscale, zshift].
+__device__ __forceinline__ void bn_finalize_backward(const BnFinal& F) {
+  float* coef = bn_coef(F.scratch, F.C);
+  const double* stripes = bn_stripes(F.scratch);
+  for (int c = threadIdx.x; c < F.C; c += blockDim.x) {
+    double dbeta, dgamma;
+    bn_sum_stripes(stripes, F.C, c, dbeta, dgamma);
+    const float mean_f = F.mean[c], invstd_f = F.invstd[c], g = F.gamma[c];
+    const double a = static_cast<double>(g) * invstd_f;
+    const double mg = dgamma * F.inv_m, mb = dbeta * F.inv_m;
+    coef[c] = static_cast<float>(a);
+    coef[F.C + c] = static_cast<float>(-a * invstd_f * mg);
+    coef[2 * F.C + c] = static_cast<float>(a * (static_cast<double>(mean_f) * invstd_f * mg - mb));
+    const float zs = __fmul_rn(g, invstd_f);
+    coef[3 * F.C + c] = zs;
+    coef[4 * F.C + c] = __fmaf_rn(-mean_f, zs, F.beta[c]);
+    F.dgamma[c] = static_cast<float>(dgamma);
+    F.dbeta[c] = static_cast<float>(dbeta);
+  }
+}
+
+}  // namespace dcfp

@@ -1,0 +1,414 @@
+// f1 -- training-mode BatchNorm2d (+ in-place ReLU) with the class-keyed sums computed by its own backward (sm_100a).
+//
+// Reference usage this replaces: nn.BatchNorm2d followed by nn.ReLU(inplace=True) (networks/backbone/resnet.py:26-56,
+// networks/tools/aspp.py:15-24) and, in loss.backward() (train.py:265), autograd's ReLU + BN backward whose
+// bn.weight.grad pruners/dcfp_pruner.py:18 reads.  Every pass below is HBM/L2-bound streaming over channels_last maps:
+//
+//   forward   F1  bn_stats_kernel: sum x, sum x^2 per channel (fp32 per thread, fp64 across blocks, striped atomics); the
+//                 last block turns them into mean / invstd / running statistics and the fp32 (scale, shift) pair
+//             F2  bn_apply_kernel: y = max(fma(x, scale, shift), 0), walking the rows backwards (what F1 read last is
+//                 what the L2 still holds)
+//   backward  B1  K1 with the fused functor: gate recomputed from the SAME fma(x, scale, shift) the forward evaluated,
+//                 dz = gate ? dy : 0, v = dz * xhat;  class rows S1[k][c] += v, S2[k][c] += v^2 (the scorer's arena)
+//                 and the totals sum dz (dbeta), sum v (dgamma) -- ONE read of (x, dy) yields the reference's score
+//                 input, the class-conditional statistics and what dx needs; the last CTA leaves the dx coefficients
+//             B2  bn_dx_kernel: dx = a * dz + b * x + d, re-reading (x, dy) -- from L2 when the layer fits (B1 loads with
+//                 normal L2 priority, B2 walks the rows in reverse order)
+//
+// No dense contraction anywhere: no tensor cores.  fp32 inside a thread / warp, fp64 across CTAs.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "bn_common.cuh"
+
+namespace dcfp {
+
+// class_stats.cu
+int k1_run_bn_backward(const dcfp_layer_desc& d, const BnFinal& fin, bool relu, cudaStream_t stream);
+
+namespace {
+
+// 16 bytes of consecutive channels of one pixel
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int kCh = 4;
+  __device__ static __forceinline__ void load(const float* p, float* v) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int kCh = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+constexpr int kBnThreads = 256;
+constexpr int kBnUnroll = 4;  // independent 16-byte loads in flight per thread and tensor
+
+struct BnArgs {
+  const void* x;
+  void* y;           // forward: y;  backward: dx
+  const void* dy;    // backward
+  const float* coef; // [5][C] left by the reduction pass: forward (scale, shift); backward (a, b, d, zscale, zshift)
+  long long M;       // pixels: N * h * w
+  int C;
+  int rows_per_block;
+};
+
+// Thread layout shared by both streaming kernels: a thread owns kCh consecutive channels (16 bytes) and walks pixel
+// rows; `cols` threads cover (a block of) a row, kBnThreads / cols rows are in flight per pass.  A block owns a
+// contiguous range of rows and walks it BACKWARDS: the pass before this one (K1) streamed the rows forwards, so the
+// end of every range is what the L2 still holds.
+struct BnThread {
+  int cols, rpp, tr, tc;
+  bool active;
+  __device__ BnThread(int lpr) {
+    cols = min(lpr, kBnThreads);
+    rpp = kBnThreads / cols;
+    tr = threadIdx.x / cols;
+    tc = threadIdx.x - tr * cols;
+    active = tr < rpp;
+  }
+};
+
+// F1: per-channel sum x, sum x^2 -> scratch stripes; the last block finalises (bn_finalize_forward).
+// 2-D grid: blockIdx.y owns a slab of 32 * kCh channels, blockIdx.x a contiguous range of rows -- fp64 atomics are scarce
+// (a launch that sent 2 * C of them from each of 592 blocks spent 15-50 us on them), so what matters is the number of ROW
+// blocks: (592 / column blocks) * 2 * C atomics per launch, ~150 k for every layer shape.
+constexpr int kStatCols = 32;
+constexpr int kStatUnroll = 8;  // 16-byte loads in flight per thread: a read-only stream needs ~2x the bytes in flight of a copy
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const BnArgs A, const BnFinal F) {
+  constexpr int kCh = Vec<T>::kCh;
+  __shared__ float red[kBnThreads * 2 * kCh];
+  const int lpr = A.C / kCh;
+  const int cols = min(lpr, kStatCols);
+  const int rpp = kBnThreads / cols;
+  const int tr = threadIdx.x / cols, tc = threadIdx.x - tr * cols;
+  const int cg = blockIdx.y * cols + tc;
+  const bool on = tr < rpp && cg < lpr;
+  const int c0 = cg * kCh;
+  const long long r0 = static_cast<long long>(blockIdx.x) * A.rows_per_block;
+  const long long r1 = min(r0 + A.rows_per_block, A.M);
+  const T* x = reinterpret_cast<const T*>(A.x);
+  float s1[kCh], s2[kCh];
+#pragma unroll
+  for (int j = 0; j < kCh; ++j) s1[j] = s2[j] = 0.f;
+  if (on) {
+    for (long long r = r0 + tr; r < r1; r += static_cast<long long>(rpp) * kStatUnroll) {
+      float v[kStatUnroll][kCh];
+#pragma unroll
+      for (int u = 0; u < kStatUnroll; ++u) {
+        const long long ru = r + static_cast<long long>(u) * rpp;
+        if (ru < r1) {
+          Vec<T>::load(x + ru * A.C + c0, v[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kCh; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kStatUnroll; ++u)
+#pragma unroll
+        for (int j = 0; j < kCh; ++j) {
+          s1[j] += v[u][j];
+          s2[j] = fmaf(v[u][j], v[u][j], s2[j]);
+        }
+    }
+  }
+  // the rpp threads that own the same channels: combine through shared memory, one fp64 atomic per channel and block
+#pragma unroll
+  for (int j = 0; j < kCh; ++j) {
+    red[(j * 2) * kBnThreads + threadIdx.x] = s1[j];
+    red[(j * 2 + 1) * kBnThreads + threadIdx.x] = s2[j];
+  }
+  __syncthreads();
+  if (on && tr == 0) {
+    for (int t = 1; t < rpp; ++t)
+#pragma unroll
+      for (int j = 0; j < kCh; ++j) {
+        s1[j] += red[(j * 2) * kBnThreads + t * cols + tc];
+        s2[j] += red[(j * 2 + 1) * kBnThreads + t * cols + tc];
+      }
+    double* stripe = bn_stripes(F.scratch) + static_cast<size_t>(blockIdx.x % kBnStripes) * 2 * A.C;
+#pragma unroll
+    for (int j = 0; j < kCh; ++j) {
+      atomicAdd(stripe + c0 + j, static_cast<double>(s1[j]));
+      atomicAdd(stripe + A.C + c0 + j, static_cast<double>(s2[j]));
+    }
+  }
+  if (bn_last_cta(bn_counter(F.scratch, F.C))) bn_finalize_forward(F);
+}
+
+// F2: y = [relu](fma(x, scale, shift)) with the coefficient pair the reduction pass left.
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A) {
+  constexpr int kCh = Vec<T>::kCh;
+  const int lpr = A.C / kCh;
+  const BnThread th(lpr);
+  const long long r0 = static_cast<long long>(blockIdx.x) * A.rows_per_block;
+  const long long r1 = min(r0 + A.rows_per_block, A.M);
+  const T* x = reinterpret_cast<const T*>(A.x);
+  T* y = reinterpret_cast<T*>(A.y);
+  for (int cb = 0; cb < lpr; cb += th.cols) {
+    const int cg = cb + th.tc;
+    if (!th.active || cg >= lpr) continue;
+    const int c0 = cg * kCh;
+    float scale[kCh], shift[kCh];
+#pragma unroll
+    for (int j = 0; j < kCh; ++j) {
+      scale[j] = A.coef[c0 + j];
+      shift[j] = A.coef[A.C + c0 + j];
+    }
+    for (long long r = r1 - 1 - th.tr; r >= r0; r -= static_cast<long long>(th.rpp) * kBnUnroll) {
+      float v[kBnUnroll][kCh];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const long long ru = r - static_cast<long long>(u) * th.rpp;
+        if (ru >= r0) Vec<T>::load(x + ru * A.C + c0, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const long long ru = r - static_cast<long long>(u) * th.rpp;
+        if (ru >= r0) {
+#pragma unroll
+          for (int j = 0; j < kCh; ++j) {
+            const float z = __fmaf_rn(v[u][j], scale[j], shift[j]);
+            v[u][j] = (RELU && z < 0.f) ? 0.f : z;  // NaN passes through, as torch.relu
+          }
+          Vec<T>::store(y + ru * A.C + c0, v[u]);
+        }
+      }
+    }
+  }
+}
+
+// B2: dx = a * dz + b * x + d per channel, with dz = (fma(x, zscale, zshift) > 0) ? dy : 0 when RELU.
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A) {
+  constexpr int kCh = Vec<T>::kCh;
+  const int lpr = A.C / kCh;
+  const BnThread th(lpr);
+  const long long r0 = static_cast<long long>(blockIdx.x) * A.rows_per_block;
+  const long long r1 = min(r0 + A.rows_per_block, A.M);
+  const T* x = reinterpret_cast<const T*>(A.x);
+  const T* dy = reinterpret_cast<const T*>(A.dy);
+  T* dx = reinterpret_cast<T*>(A.y);
+  for (int cb = 0; cb < lpr; cb += th.cols) {
+    const int cg = cb + th.tc;
+    if (!th.active || cg >= lpr) continue;
+    const int c0 = cg * kCh;
+    float zs[kCh], zt[kCh], ca[kCh], cb_[kCh], cd[kCh];
+#pragma unroll
+    for (int j = 0; j < kCh; ++j) {
+      ca[j] = A.coef[c0 + j];
+      cb_[j] = A.coef[A.C + c0 + j];
+      cd[j] = A.coef[2 * A.C + c0 + j];
+      zs[j] = A.coef[3 * A.C + c0 + j];
+      zt[j] = A.coef[4 * A.C + c0 + j];
+    }
+    for (long long r = r1 - 1 - th.tr; r >= r0; r -= static_cast<long long>(th.rpp) * kBnUnroll) {
+      float vx[kBnUnroll][kCh], vg[kBnUnroll][kCh];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const long long ru = r - static_cast<long long>(u) * th.rpp;
+        if (ru >= r0) {
+          Vec<T>::load(x + ru * A.C + c0, vx[u]);
+          Vec<T>::load(dy + ru * A.C + c0, vg[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const long long ru = r - static_cast<long long>(u) * th.rpp;
+        if (ru >= r0) {
+#pragma unroll
+          for (int j = 0; j < kCh; ++j) {
+            float dz = vg[u][j];
+            if (RELU) dz = __fmaf_rn(vx[u][j], zs[j], zt[j]) > 0.f ? dz : 0.f;
+            vg[u][j] = fmaf(ca[j], dz, fmaf(cb_[j], vx[u][j], cd[j]));
+          }
+          Vec<T>::store(dx + ru * A.C + c0, vg[u]);
+        }
+      }
+    }
+  }
+}
+
+int validate_bn(const dcfp_bn_desc* d, bool backward) {
+  DCFP_REQUIRE(d != nullptr, DCFP_EINVAL, "bn: null descriptor");
+  DCFP_REQUIRE(d->x && d->gamma && d->beta && d->mean && d->invstd && d->scratch, DCFP_EINVAL, "bn: null pointer (x/gamma/beta/mean/invstd/scratch)");
+  DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->scratch) % 8 == 0, DCFP_EINVAL, "bn: scratch must be 8-byte aligned");
+  DCFP_REQUIRE(d->N > 0 && d->C > 0 && d->h > 0 && d->w > 0, DCFP_EINVAL, "bn: bad extent N=%d C=%d h=%d w=%d", d->N, d->C, d->h, d->w);
+  DCFP_REQUIRE(d->dtype == DCFP_F32 || d->dtype == DCFP_BF16, DCFP_EINVAL, "bn: unknown dtype %d", d->dtype);
+  DCFP_REQUIRE(d->phases >= 0 && d->phases <= 2 && d->reserved == 0, DCFP_EINVAL, "bn: bad phases (%d) / reserved field", d->phases);
+  const int kch = d->dtype == DCFP_F32 ? 4 : 8;
+  DCFP_REQUIRE(d->C % kch == 0, DCFP_EUNSUPPORTED, "bn: C=%d must be a multiple of %d (16-byte channel vectors)", d->C, kch);
+  DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->x) % 16 == 0, DCFP_EUNSUPPORTED, "bn: x must be 16-byte aligned");
+  if (!backward) {
+    DCFP_REQUIRE(d->y != nullptr && reinterpret_cast<uintptr_t>(d->y) % 16 == 0, DCFP_EINVAL, "bn_forward: y null or unaligned");
+    DCFP_REQUIRE((d->running_mean == nullptr) == (d->running_var == nullptr), DCFP_EINVAL, "bn_forward: running_mean/var must come together");
+  } else {
+    DCFP_REQUIRE(d->dy && d->S1 && d->S2 && d->dgamma && d->dbeta, DCFP_EINVAL, "bn_backward: null pointer (dy/S1/S2/dgamma/dbeta)");
+    DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->dy) % 16 == 0 && reinterpret_cast<uintptr_t>(d->dx) % 16 == 0, DCFP_EUNSUPPORTED,
+                 "bn_backward: dy / dx must be 16-byte aligned");
+    DCFP_REQUIRE(d->K >= 1 && d->K <= DCFP_MAX_CLASSES && (d->keys != nullptr || d->K == 1), DCFP_EINVAL, "bn_backward: bad K / keys");
+  }
+  return 0;
+}
+
+// grid of the streaming kernels: `per_sm` blocks per SM, each owning a contiguous range of whole row passes
+template <typename T>
+BnArgs plan_rows(const BnArgs& A0, int per_sm, dim3* grid) {
+  BnArgs A = A0;
+  constexpr int kCh = Vec<T>::kCh;
+  const int lpr = A.C / kCh;
+  const int cols = std::min(lpr, kBnThreads);
+  const int rpp = kBnThreads / cols;
+  const long long passes = (A.M + rpp - 1) / rpp;
+  long long blocks = std::min<long long>(static_cast<long long>(per_sm) * num_sms(), (passes + kBnUnroll - 1) / kBnUnroll);
+  blocks = std::max<long long>(blocks, 1);
+  long long rows = (A.M + blocks - 1) / blocks;
+  rows = (rows + rpp - 1) / rpp * rpp;
+  A.rows_per_block = static_cast<int>(rows);
+  *grid = dim3(static_cast<unsigned>((A.M + rows - 1) / rows));
+  return A;
+}
+
+BnArgs stream_args(const dcfp_bn_desc* d) {
+  BnArgs A{};
+  A.x = d->x;
+  A.coef = bn_coef(d->scratch, d->C);
+  A.M = static_cast<long long>(d->N) * d->h * d->w;
+  A.C = d->C;
+  return A;
+}
+
+BnFinal final_args(const dcfp_bn_desc* d) {
+  BnFinal F{};
+  const long long M = static_cast<long long>(d->N) * d->h * d->w;
+  F.scratch = d->scratch;
+  F.gamma = d->gamma, F.beta = d->beta;
+  F.mean = d->mean, F.invstd = d->invstd;
+  F.running_mean = d->running_mean, F.running_var = d->running_var;
+  F.dgamma = d->dgamma, F.dbeta = d->dbeta;
+  F.inv_m = 1.0 / static_cast<double>(M);
+  F.unbias = M > 1 ? static_cast<double>(M) / static_cast<double>(M - 1) : 1.0;
+  F.eps = d->eps, F.momentum = d->momentum;
+  F.C = d->C;
+  return F;
+}
+
+template <typename T>
+int forward_t(const dcfp_bn_desc* d, cudaStream_t stream) {
+  BnArgs A = stream_args(d);
+  dim3 grid;
+  if (d->phases != 2) {
+    // row blocks x column blocks ~ 4 blocks per SM; every block walks whole unrolled passes of its rows
+    constexpr int kCh = Vec<T>::kCh;
+    const int lpr = A.C / kCh;
+    const int cols = std::min(lpr, kStatCols);
+    const int rpp = kBnThreads / cols;
+    const int col_blocks = (lpr + cols - 1) / cols;
+    const long long passes = (A.M + static_cast<long long>(rpp) * kStatUnroll - 1) / (static_cast<long long>(rpp) * kStatUnroll);
+    long long row_blocks = std::max<long long>(1, std::min<long long>(6LL * num_sms() / col_blocks, passes));
+    long long rows = (A.M + row_blocks - 1) / row_blocks;
+    rows = (rows + rpp - 1) / rpp * rpp;
+    BnArgs S = A;
+    S.rows_per_block = static_cast<int>(rows);
+    grid = dim3(static_cast<unsigned>((A.M + rows - 1) / rows), static_cast<unsigned>(col_blocks));
+    bn_stats_kernel<T><<<grid, kBnThreads, 0, stream>>>(S, final_args(d));
+    const int rc = finish_launch("bn_stats");
+    if (rc || d->phases == 1) return rc;
+  }
+  A.y = d->y;
+  const BnArgs P = plan_rows<T>(A, 4, &grid);
+  if (d->relu) bn_apply_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P);
+  else bn_apply_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P);
+  return finish_launch("bn_apply");
+}
+
+template <typename T>
+int backward_dx_t(const dcfp_bn_desc* d, cudaStream_t stream) {
+  BnArgs A = stream_args(d);
+  A.dy = d->dy;
+  A.y = d->dx;
+  dim3 grid;
+  const BnArgs P = plan_rows<T>(A, 2, &grid);
+  if (d->relu) bn_dx_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P);
+  else bn_dx_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P);
+  return finish_launch("bn_dx");
+}
+
+}  // namespace
+}  // namespace dcfp
+
+extern "C" int dcfp_bn_supported(int N, int C, int h, int w, int dtype) {
+  const int kch = dtype == DCFP_F32 ? 4 : 8;
+  if (dtype != DCFP_F32 && dtype != DCFP_BF16) return 0;
+  if (N <= 0 || C <= 0 || h <= 0 || w <= 0 || C % kch != 0) return 0;
+  return static_cast<long long>(N) * h * w >= 64 ? 1 : 0;  // tiny pooled maps stay with the generic K1 path
+}
+
+extern "C" size_t dcfp_bn_scratch_bytes(int C) { return C > 0 ? dcfp::bn_scratch_bytes(C) : 0; }
+
+extern "C" int dcfp_bn_forward(const dcfp_bn_desc* d, void* stream_) {
+  using namespace dcfp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int rc = validate_bn(d, false);
+  if (rc) return rc;
+  DCFP_REQUIRE(dcfp_bn_supported(d->N, d->C, d->h, d->w, d->dtype), DCFP_EUNSUPPORTED, "bn_forward: map not eligible (see dcfp_bn_supported)");
+  return d->dtype == DCFP_F32 ? forward_t<float>(d, stream) : forward_t<__nv_bfloat16>(d, stream);
+}
+
+extern "C" int dcfp_bn_backward(const dcfp_bn_desc* d, void* stream_) {
+  using namespace dcfp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = validate_bn(d, true);
+  if (rc) return rc;
+  if (d->phases != 2) {
+    dcfp_layer_desc L{};
+    L.x = d->x;
+    L.N = d->N, L.C = d->C, L.h = d->h, L.w = d->w;
+    L.dtype = d->dtype;
+    L.layout = DCFP_NHWC;
+    L.dy = d->dy;
+    L.scale = d->invstd;
+    L.shift = d->mean;
+    L.affine_mode = DCFP_AFFINE_INVSTD_MEAN;
+    L.keys = d->keys;
+    L.K = d->K;
+    L.S1 = d->S1, L.S2 = d->S2;
+    L.ld = d->ld > 0 ? d->ld : d->C;
+    // the dx pass re-reads (x, dy): keep them in the 126 MB L2 when the pair can fit
+    const long long bytes = 2LL * d->N * d->C * d->h * d->w * (d->dtype == DCFP_F32 ? 4 : 2);
+    L.hints = ((d->dx != nullptr || d->phases == 1) && bytes <= (96LL << 20)) ? DCFP_HINT_KEEP_L2 : 0;
+    rc = k1_run_bn_backward(L, final_args(d), d->relu != 0, stream);  // B1 (+ finalisation by its last CTA)
+    if (rc || d->phases == 1) return rc;
+  }
+  if (d->dx == nullptr) return 0;  // dgamma / dbeta were written by B1's last CTA
+  return d->dtype == DCFP_F32 ? backward_dx_t<float>(d, stream) : backward_dx_t<__nv_bfloat16>(d, stream);
+}

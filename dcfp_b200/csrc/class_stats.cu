@@ -116,7 +116,7 @@ int validate(const dcfp_layer_desc& d, int idx) {
                "class_stats[%d]: unknown affine_mode %d", idx, d.affine_mode);
   DCFP_REQUIRE(d.affine_mode == DCFP_AFFINE_SCALE_SHIFT || (d.scale && d.shift), DCFP_EINVAL,
                "class_stats[%d]: DCFP_AFFINE_INVSTD_MEAN needs both scale (invstd) and shift (mean)", idx);
-  DCFP_REQUIRE(d.reserved == 0, DCFP_EINVAL, "class_stats[%d]: reserved field must be 0", idx);
+  DCFP_REQUIRE((d.hints & ~DCFP_HINT_KEEP_L2) == 0, DCFP_EINVAL, "class_stats[%d]: unknown bits in hints (%d)", idx, d.hints);
   DCFP_REQUIRE(d.keys != nullptr || d.K == 1, DCFP_EINVAL, "class_stats[%d]: keys == NULL requires K == 1", idx);
   DCFP_REQUIRE(static_cast<long long>(d.h) * d.w < (1LL << 30), DCFP_ETOOBIG, "class_stats[%d]: plane too large", idx);
   DCFP_REQUIRE(static_cast<long long>(d.N) * d.C < (1LL << 31), DCFP_ETOOBIG, "class_stats[%d]: too many planes", idx);
@@ -170,24 +170,28 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
       const int v = e ? atoi(e) : 0;
       return v >= 1 && v <= 64 ? v : 8;
     }();
-    long long target = std::min<long long>(8 << 20, std::max<long long>(128 << 10, nhwc_bytes / (static_cast<long long>(tiles_per_cta) * kNumSMs)));
+    NhwcPlan plan;
+    plan.target_bytes = std::min<long long>(8 << 20, std::max<long long>(128 << 10, nhwc_bytes / (static_cast<long long>(tiles_per_cta) * num_sms())));
+    // a lone layer (per-layer launches): exactly one tile per persistent CTA
+    plan.single_wave = n_nhwc == 1;
+    plan.keep_l2 = (descs[nhwc[0]].hints & DCFP_HINT_KEEP_L2) != 0;
     const int nhwc_big = bwd ? kNhwcBigGroupBwd : kNhwcBigGroupFwd;
     for (int first = 0; first < n_nhwc;) {
       const int m = std::min(n_nhwc - first, nhwc_big);
       int rc;
       if (m <= kSmallGroup) {
         if (dtype == DCFP_F32)
-          rc = bwd ? run_nhwc<float, true, kSmallGroup>(descs, nhwc + first, m, target, stream)
-                   : run_nhwc<float, false, kSmallGroup>(descs, nhwc + first, m, target, stream);
+          rc = bwd ? run_nhwc<float, true, kSmallGroup>(descs, nhwc + first, m, plan, stream)
+                   : run_nhwc<float, false, kSmallGroup>(descs, nhwc + first, m, plan, stream);
         else
-          rc = bwd ? run_nhwc<__nv_bfloat16, true, kSmallGroup>(descs, nhwc + first, m, target, stream)
-                   : run_nhwc<__nv_bfloat16, false, kSmallGroup>(descs, nhwc + first, m, target, stream);
+          rc = bwd ? run_nhwc<__nv_bfloat16, true, kSmallGroup>(descs, nhwc + first, m, plan, stream)
+                   : run_nhwc<__nv_bfloat16, false, kSmallGroup>(descs, nhwc + first, m, plan, stream);
       } else if (dtype == DCFP_F32) {
-        rc = bwd ? run_nhwc<float, true, kNhwcBigGroupBwd>(descs, nhwc + first, m, target, stream)
-                 : run_nhwc<float, false, kNhwcBigGroupFwd>(descs, nhwc + first, m, target, stream);
+        rc = bwd ? run_nhwc<float, true, kNhwcBigGroupBwd>(descs, nhwc + first, m, plan, stream)
+                 : run_nhwc<float, false, kNhwcBigGroupFwd>(descs, nhwc + first, m, plan, stream);
       } else {
-        rc = bwd ? run_nhwc<__nv_bfloat16, true, kNhwcBigGroupBwd>(descs, nhwc + first, m, target, stream)
-                 : run_nhwc<__nv_bfloat16, false, kNhwcBigGroupFwd>(descs, nhwc + first, m, target, stream);
+        rc = bwd ? run_nhwc<__nv_bfloat16, true, kNhwcBigGroupBwd>(descs, nhwc + first, m, plan, stream)
+                 : run_nhwc<__nv_bfloat16, false, kNhwcBigGroupFwd>(descs, nhwc + first, m, plan, stream);
       }
       if (rc) return rc;
       first += m;
@@ -196,7 +200,7 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
   if (n_tiled == 0) return 0;
   // chunk length: ~512 KB per CTA, shortened while the call cannot fill ~4 waves of 4 CTAs/SM
   int chunk = kTargetBoxesPerChunk;
-  while (chunk > 16 && total_boxes / chunk < 4LL * 4 * kNumSMs) chunk >>= 1;
+  while (chunk > 16 && total_boxes / chunk < 4LL * 4 * num_sms()) chunk >>= 1;
 
   const int big = bwd ? kBigGroupBwd : kBigGroupFwd;
   for (int first = 0; first < n_tiled;) {
@@ -223,6 +227,28 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// ---- internal entry points used by bn_fused.cu ---------------------------------------------------------------------
+// BN backward, first pass: class-keyed S1/S2 of v = dz * xhat, the per-channel totals (sum dz, sum dz * xhat) into the
+// scratch stripes, and -- by the last CTA -- dgamma / dbeta and the dx coefficients (bn_common.cuh)
+int k1_run_bn_backward(const dcfp_layer_desc& d, const BnFinal& fin, bool relu, cudaStream_t stream) {
+  int rc = validate(d, 0);
+  if (rc) return rc;
+  DCFP_REQUIRE(d.dy != nullptr && d.affine_mode == DCFP_AFFINE_INVSTD_MEAN && nhwc_ok(d), DCFP_EUNSUPPORTED,
+               "bn_backward: needs a channels_last fp32/bf16 map with C %% 4 == 0, 16-byte aligned, >= 64 pixels");
+  DCFP_REQUIRE(fin.scratch != nullptr && fin.gamma && fin.beta, DCFP_EINVAL, "bn_backward: null scratch / gamma / beta");
+  NhwcPlan plan;
+  plan.single_wave = true;
+  plan.keep_l2 = (d.hints & DCFP_HINT_KEEP_L2) != 0;
+  const NhwcFused F{fin.gamma, fin.beta, fin};
+  const int which = 0;
+  if (d.dtype == DCFP_F32)
+    return relu ? run_nhwc<float, true, kSmallGroup, 2>(&d, &which, 1, plan, stream, &F)
+                : run_nhwc<float, true, kSmallGroup, 1>(&d, &which, 1, plan, stream, &F);
+  return relu ? run_nhwc<__nv_bfloat16, true, kSmallGroup, 2>(&d, &which, 1, plan, stream, &F)
+              : run_nhwc<__nv_bfloat16, true, kSmallGroup, 1>(&d, &which, 1, plan, stream, &F);
+}
+
 }  // namespace dcfp
 
 extern "C" int dcfp_class_stats(const dcfp_layer_desc* desc_host, void* stream) {
@@ -242,7 +268,7 @@ extern "C" int dcfp_label_keys(const void* label, int label_dtype, int N, int H0
   DCFP_REQUIRE(label_dtype >= DCFP_LABEL_U8 && label_dtype <= DCFP_LABEL_I64, DCFP_EINVAL, "label_keys: unknown label dtype %d",
                label_dtype);
   const long long total = static_cast<long long>(N) * h * w;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4LL * kNumSMs));
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4LL * num_sms()));
   label_keys_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       label, label_dtype, N, H0, W0, h, w, K, static_cast<float>(H0) / static_cast<float>(h),
       static_cast<float>(W0) / static_cast<float>(w), keys, cnt);

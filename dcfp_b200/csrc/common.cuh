@@ -15,7 +15,9 @@ int cuda_fail(cudaError_t e, const char* what);
 // opt a kernel into > 48 KB dynamic shared memory once per (kernel, device)
 int ensure_smem(const void* func, int bytes);
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (compile-time default for table sizing)
+// SM count of the current device (queried once per device; persistent grids are sized with it)
+int num_sms();
 
 #define DCFP_REQUIRE(cond, code, ...) \
   do {                                \
@@ -58,6 +60,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "bn_common.cuh"
 #include "k1_common.cuh"
 
 namespace dcfp {
@@ -58,7 +59,16 @@ struct NhwcParams {
   int32_t tile_prefix[MAXL + 1];
   int32_t n_layers;
   int32_t K;
-  int32_t stages;  // boxes in flight per warp
+  int32_t stages;   // boxes in flight per warp
+  int32_t keep_l2;  // 0: read-once stream (evict-first); 1: a second pass re-reads these maps (normal L2 priority)
+};
+// BN-backward fusion (FUSED != 0; one layer per launch): the value functor becomes v = dz * xhat with the ReLU gate
+// recomputed from the forward's own z = fma(x, zscale, zshift) (FUSED == 2), and the launch also yields the two
+// per-channel totals every BN backward needs before it can write dx:  tot[0][c] += sum dz,  tot[1][c] += sum dz * xhat.
+struct NhwcFused {
+  const float* gamma;  // [C]  z = fma(x, zs, zt) with zs = gamma * invstd, zt = fma(-mean, zs, beta): the SAME fp32
+  const float* beta;   // [C]  expressions the forward evaluated, so the gate equals "forward output > 0" bit for bit
+  BnFinal fin;         // scratch (totals go to its stripes) + what the last CTA needs to finalise the backward
 };
 constexpr int kNhwcBigGroupFwd = 128;  // 128 * (128 + 72) B = 25.0 KB of kernel parameters
 constexpr int kNhwcBigGroupBwd = 80;   //  80 * (256 + 72) B = 25.6 KB
@@ -88,9 +98,10 @@ struct BoxRow<__nv_bfloat16> {
 
 constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-boxes, or 2 (x, dy) pairs
 
-template <typename T, bool BWD, bool AFFINE, int MAXL>
+template <typename T, bool BWD, bool AFFINE, int MAXL, int FUSED = 0>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
-    class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P) {
+    class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P, const NhwcFused F) {
+  static_assert(FUSED == 0 || BWD, "the fused BN-backward functor reads x and dy");
   constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)));
   constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   const uint32_t lane_off = static_cast<uint32_t>(lane * BoxRow<T>::kLaneBytes);
   const unsigned dropped = K * 0x01010101u;
   const bool direct = K <= static_cast<unsigned>(kNhwcSlots);  // slot == class, no tags
-  const uint64_t policy = policy_evict_first();
+  const uint64_t policy = P.keep_l2 ? policy_evict_normal() : policy_evict_first();
 
   if (lane < kStages) mbar_init(my_bars + lane * 8, 1);
   for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -129,6 +140,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   double* out2 = nullptr;
   size_t ld = 0;
   f2 sc01 = pack2(1.f, 1.f), sc23 = sc01, sf01 = 0, sf23 = 0;
+  f2 zs01 = 0, zs23 = 0, zt01 = 0, zt23 = 0;  // FUSED == 2: z = x * zs + zt (the forward's pre-ReLU output)
+  f2 tb01 = 0, tb23 = 0, tg01 = 0, tg23 = 0;  // FUSED: per-lane totals  sum dz,  sum dz * xhat  of the current slab
   // slot cache: lane i (< kNhwcSlots) holds the class of row i (kFree = none); round-robin victim; last hit
   constexpr unsigned kFree = 0xffffffffu;
   unsigned my_tag = kFree, used = 0;  // `used`: CLOCK reference bits of the rows (warp-uniform)
@@ -138,8 +151,18 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   const uint32_t mine_u32 = smem_u32(mine);
 
   auto row_to_arena = [&](int slot, unsigned cls) {  // fp32 row -> fp64 arena, row zeroed
-    const float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
-    if (lane_on) {
+    float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
+    if (fold2) {  // lanes 16-31 hold the same 64 channels (odd pixels): one atomic per channel, not two
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
+      a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
+      a.z += __shfl_xor_sync(0xffffffffu, a.z, 16);
+      a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
+      b.x += __shfl_xor_sync(0xffffffffu, b.x, 16);
+      b.y += __shfl_xor_sync(0xffffffffu, b.y, 16);
+      b.z += __shfl_xor_sync(0xffffffffu, b.z, 16);
+      b.w += __shfl_xor_sync(0xffffffffu, b.w, 16);
+    }
+    if (lane_on && !(fold2 && lane >= 16)) {
       double* d1 = out1 + cls * ld;
       double* d2 = out2 + cls * ld;
       if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));
@@ -200,14 +223,93 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     if (BWD) {
       f2 da, db;
       BoxRow<T>::load(box_lane + kNhwcBoxBytes, row, da, db);
+      if (FUSED == 2) {  // dz = dy where the forward's ReLU let the value through (z > 0, strict -- threshold_backward)
+        const f2 za = fma2(a, zs01, zt01), zb = fma2(b, zs23, zt23);
+        da = pack2(lo2(za) > 0.f ? lo2(da) : 0.f, hi2(za) > 0.f ? hi2(da) : 0.f);
+        db = pack2(lo2(zb) > 0.f ? lo2(db) : 0.f, hi2(zb) > 0.f ? hi2(db) : 0.f);
+      }
       a = mul2(da, fma2(a, sc01, sf01));
       b = mul2(db, fma2(b, sc23, sf23));
+      if (FUSED) {
+        tb01 = add2(tb01, da);
+        tb23 = add2(tb23, db);
+        tg01 = add2(tg01, a);
+        tg23 = add2(tg23, b);
+      }
     } else if (AFFINE) {
       a = fma2(a, sc01, sf01);
       b = fma2(b, sc23, sf23);
     }
   };
-  auto fold = [&]() {  // every row of this warp -> arena (end of a (layer, slab group))
+  // End of a (layer, slab group): rows -> arena.  The warps of a CTA that share a slab (phases > 1) first merge their
+  // rows pairwise into the lowest one (tree over the phases, through shared memory), so the arena sees ONE atomic per
+  // (class, channel) and CTA instead of one per warp: same-address fp64 atomics serialise at ~38 cycles each in L2, which
+  // a per-layer launch (fused BN) pays in full at its tail.  Every warp of the CTA reaches fold() at the same tile
+  // boundaries, so the CTA barriers below are uniform.  Publishing area: the warp's own staging buffer (idle here).
+  auto fold = [&]() {
+    if (phases > 1) {
+      const int spc_ = kNhwcWarps / phases;
+      auto pub = [&](int w) { return reinterpret_cast<unsigned*>(smem + static_cast<size_t>(w) * kStages * kStageBytes); };
+      for (int step = 1; step < phases; step <<= 1) {
+        if ((phase & (2 * step - 1)) == step) {  // donor of this round
+          if (!direct && lane < kNhwcSlots) pub(warp)[lane] = my_tag;
+          if (FUSED) {
+            f2* t = reinterpret_cast<f2*>(pub(warp) + 32) + lane * 4;
+            t[0] = tb01, t[1] = tb23, t[2] = tg01, t[3] = tg23;
+          }
+        }
+        __syncthreads();
+        if ((phase & (2 * step - 1)) == 0 && phase + step < phases) {  // receiver: merge the donor's rows into mine
+          const int d = warp + step * spc_;
+          const float4* drow = reinterpret_cast<const float4*>(slots + static_cast<size_t>(d) * kNhwcSlots * 256) + lane;
+          const int n_rows = direct ? static_cast<int>(K) : kNhwcSlots;
+          for (int i = 0; i < n_rows; ++i) {
+            const unsigned cls = direct ? static_cast<unsigned>(i) : pub(d)[i];
+            if (cls == kFree) continue;
+            const float4 a = drow[i * 64], b = drow[i * 64 + 32];
+            row_add(cls, pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+          }
+          if (FUSED) {
+            const f2* t = reinterpret_cast<const f2*>(pub(d) + 32) + lane * 4;
+            tb01 = add2(tb01, t[0]);
+            tb23 = add2(tb23, t[1]);
+            tg01 = add2(tg01, t[2]);
+            tg23 = add2(tg23, t[3]);
+          }
+        }
+        __syncthreads();
+        if ((phase & (2 * step - 1)) == step) {  // the donor's sums now live in the receiver
+          for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+          my_tag = kFree;
+          victim = 0;
+          used = 0;
+          last_key = 0xffffffffu;
+          tb01 = tb23 = tg01 = tg23 = 0;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes above, TMA writes next
+    }
+    if (FUSED) {
+      if (fold2) {
+        tb01 = add2(tb01, __shfl_xor_sync(0xffffffffu, tb01, 16));
+        tb23 = add2(tb23, __shfl_xor_sync(0xffffffffu, tb23, 16));
+        tg01 = add2(tg01, __shfl_xor_sync(0xffffffffu, tg01, 16));
+        tg23 = add2(tg23, __shfl_xor_sync(0xffffffffu, tg23, 16));
+      }
+      if (lane_on && !(fold2 && lane >= 16) && (tb01 | tb23 | tg01 | tg23) != 0) {
+        double* t0 = bn_stripes(F.fin.scratch) + static_cast<size_t>(blockIdx.x % kBnStripes) * 2 * F.fin.C + c0;
+        double* t1 = t0 + F.fin.C;
+        atomicAdd(t0 + 0, static_cast<double>(lo2(tb01)));
+        atomicAdd(t0 + 1, static_cast<double>(hi2(tb01)));
+        atomicAdd(t0 + 2, static_cast<double>(lo2(tb23)));
+        atomicAdd(t0 + 3, static_cast<double>(hi2(tb23)));
+        atomicAdd(t1 + 0, static_cast<double>(lo2(tg01)));
+        atomicAdd(t1 + 1, static_cast<double>(hi2(tg01)));
+        atomicAdd(t1 + 2, static_cast<double>(lo2(tg23)));
+        atomicAdd(t1 + 3, static_cast<double>(hi2(tg23)));
+      }
+      tb01 = tb23 = tg01 = tg23 = 0;
+    }
     if (direct) {
       for (unsigned k = 0; k < K; ++k) row_to_arena(static_cast<int>(k), k);
     } else {
@@ -258,6 +360,18 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
         sc23 = pack2(sc[2], sc[3]);
         sf01 = pack2(sf[0], sf[1]);
         sf23 = pack2(sf[2], sf[3]);
+      }
+      if (FUSED == 2 && lane_on) {  // needs scale = invstd, shift = mean (DCFP_AFFINE_INVSTD_MEAN)
+        float zs[4], zt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          zs[j] = __fmul_rn(F.gamma[c0 + j], L.scale[c0 + j]);
+          zt[j] = __fmaf_rn(-L.shift[c0 + j], zs[j], F.beta[c0 + j]);
+        }
+        zs01 = pack2(zs[0], zs[1]);
+        zs23 = pack2(zs[2], zs[3]);
+        zt01 = pack2(zt[0], zt[1]);
+        zt23 = pack2(zt[2], zt[3]);
       }
     }
 
@@ -435,6 +549,9 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     }
   }
   if (cur_layer >= 0) fold();
+  if (FUSED) {  // the last CTA turns the stripes into dgamma / dbeta and the dx coefficients
+    if (bn_last_cta(bn_counter(F.fin.scratch, F.fin.C))) bn_finalize_backward(F.fin);
+  }
 }
 
 // NHWC: [rows = N*HW][cols = C], box = [G px][128 channels], no swizzle (a pixel row is read with one LDS per lane)
@@ -466,15 +583,27 @@ bool nhwc_ok(const dcfp_layer_desc& d) {
   return true;
 }
 
-template <typename T, bool BWD, int MAXL>
-int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long target_bytes, cudaStream_t stream) {
+// Launch plan knobs of one NHWC call.  single_wave: every layer is cut into <= (#SMs / slab groups) chunks so that the
+// whole call is ONE tile per persistent CTA (per-layer launches of the fused BN path: a second tile would restart the
+// TMA pipeline and a 149th tile would double the runtime).  keep_l2: a second pass re-reads the maps.
+struct NhwcPlan {
+  long long target_bytes = 1 << 20;
+  bool single_wave = false;
+  bool keep_l2 = false;
+};
+
+template <typename T, bool BWD, int MAXL, int FUSED = 0>
+int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPlan& plan, cudaStream_t stream,
+             const NhwcFused* fused = nullptr) {
   constexpr int kTens = BWD ? 2 : 1;
   constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)));
   constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   const int K = descs[which[0]].K;
+  const int sms = num_sms();
   NhwcParams<MAXL, kTens> P;
   P.n_layers = n;
   P.K = K;
+  P.keep_l2 = plan.keep_l2 ? 1 : 0;
   P.tile_prefix[0] = 0;
   bool affine = false;
   for (int i = 0; i < n; ++i) {
@@ -498,14 +627,34 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
     }
     const int n_slabs = (L.C + kNhwcSlab - 1) / kNhwcSlab;
     int spc = 1;
-    while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
+    // per-layer launches put all 8 warps of a CTA on ONE slab (they merge their rows before touching the arena: 8x fewer
+    // of the scarce fp64 atomics, nothing to overlap them with at the tail of a short launch); grouped launches spread the
+    // warps over up to 8 slabs (whole 4 KB rows per CTA, folds are rare there)
+    static const int wide = []() {
+      const char* e = getenv("DCFP_K1_SINGLE_WAVE_WIDE");
+      return e ? atoi(e) : 0;
+    }();
+    if (!plan.single_wave || wide)
+      while (spc < kNhwcWarps && spc < n_slabs) spc <<= 1;
     L.spc = spc;
     L.n_slab_groups = (n_slabs + spc - 1) / spc;
-    const int gran = G * (kNhwcWarps / spc);  // every phase gets whole pixel groups
-    const long long row_bytes = static_cast<long long>(std::min(L.C, spc * kNhwcSlab)) * sizeof(T);
-    long long px = std::max<long long>(target_bytes / row_bytes, gran);
-    px = (px + gran - 1) / gran * gran;
-    L.px_per_chunk = static_cast<int>(std::min<long long>(px, (static_cast<long long>(L.n_px) + gran - 1) / gran * gran));
+    static const int no_single = []() {
+      const char* e = getenv("DCFP_K1_NO_SINGLE_WAVE");
+      return e ? atoi(e) : 0;
+    }();
+    if (plan.single_wave && !no_single) {
+      // chunks of whole boxes (G rows); the phases of a chunk may differ by one box
+      const int chunks = std::max(1, sms / (L.n_slab_groups * n));
+      long long px = (static_cast<long long>(L.n_px) + chunks - 1) / chunks;
+      px = std::max<long long>((px + G - 1) / G * G, G);
+      L.px_per_chunk = static_cast<int>(px);
+    } else {
+      const int gran = G * (kNhwcWarps / spc);  // every phase gets whole pixel groups
+      const long long row_bytes = static_cast<long long>(std::min(L.C, spc * kNhwcSlab)) * sizeof(T);
+      long long px = std::max<long long>(plan.target_bytes / row_bytes, gran);
+      px = (px + gran - 1) / gran * gran;
+      L.px_per_chunk = static_cast<int>(std::min<long long>(px, (static_cast<long long>(L.n_px) + gran - 1) / gran * gran));
+    }
     L.n_chunks = (L.n_px + L.px_per_chunk - 1) / L.px_per_chunk;
     const long long tiles = static_cast<long long>(L.n_chunks) * L.n_slab_groups;
     DCFP_REQUIRE(P.tile_prefix[i] + tiles < (1LL << 31), DCFP_ETOOBIG, "class_stats: too many tiles");
@@ -522,14 +671,24 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, long long ta
   }();
   P.stages = kNhwcStageBudget / (kTens * kNhwcBoxBytes);
   if (forced >= 1 && forced * kTens * kNhwcBoxBytes <= (20 << 10)) P.stages = forced;
+  static const int force_keep = []() {
+    const char* e = getenv("DCFP_K1_KEEP_L2");
+    return e ? atoi(e) : -1;
+  }();
+  if (force_keep >= 0) P.keep_l2 = force_keep;
   const size_t smem = static_cast<size_t>(kNhwcWarps) * P.stages * kTens * kNhwcBoxBytes +
                       static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float) + 8 * kNhwcWarps * P.stages +
                       1024 /* base alignment slack */;
-  void (*kern)(NhwcParams<MAXL, kTens>) = class_stats_nhwc_kernel<T, BWD, true, MAXL>;
-  if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL>;
+  void (*kern)(NhwcParams<MAXL, kTens>, NhwcFused) = class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED>;
+  if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL, 0>;
+  NhwcFused F{};
+  if (FUSED) {
+    DCFP_REQUIRE(fused != nullptr && n == 1 && fused->fin.scratch != nullptr, DCFP_EINVAL, "class_stats: fused BN backward needs one layer");
+    F = *fused;
+  }
   int rc = ensure_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
   if (rc) return rc;
-  kern<<<std::min(n_tiles, kNumSMs), kNhwcWarps * 32, smem, stream>>>(P);  // persistent: one CTA per SM
+  kern<<<std::min(n_tiles, sms), kNhwcWarps * 32, smem, stream>>>(P, F);  // persistent: one CTA per SM
   return finish_launch("class_stats_nhwc");
 }
 

@@ -363,6 +363,95 @@ std::tuple<Tensor, Tensor> class_balance_weights(const Tensor& label, int64_t K,
   return {weight, counts.slice(1, 0, K)};
 }
 
+// ---- f1: fused training-mode BatchNorm2d (+ReLU) ------------------------------------------------------------------
+const float* chan_f32(const Tensor& t, int64_t C, const char* name) {
+  require_cuda(t, name);
+  TORCH_CHECK(t.scalar_type() == at::kFloat && t.is_contiguous() && t.numel() == C, "dcfp::bn: `", name, "` must be a contiguous fp32 [C] tensor");
+  return t.data_ptr<float>();
+}
+dcfp_bn_desc bn_desc(const Tensor& x, const Tensor& gamma, const Tensor& beta, const Tensor& mean, const Tensor& invstd,
+                     const Tensor& sums, bool relu) {
+  require_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "dcfp::bn: x must be a channels_last [N,C,h,w] tensor");
+  TORCH_CHECK(x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16, "dcfp::bn: x must be fp32 or bf16");
+  const int64_t C = x.size(1);
+  dcfp_bn_desc d{};
+  d.x = x.data_ptr();
+  d.gamma = chan_f32(gamma, C, "gamma");
+  d.beta = chan_f32(beta, C, "beta");
+  d.mean = const_cast<float*>(chan_f32(mean, C, "mean"));
+  d.invstd = const_cast<float*>(chan_f32(invstd, C, "invstd"));
+  require_cuda(sums, "scratch");
+  TORCH_CHECK(sums.scalar_type() == at::kDouble && sums.is_contiguous() &&
+                  static_cast<size_t>(sums.numel()) * sizeof(double) >= dcfp_bn_scratch_bytes(static_cast<int>(C)),
+              "dcfp::bn: scratch must be a contiguous, zeroed fp64 tensor of at least bn_scratch_bytes(C) bytes");
+  d.scratch = sums.data_ptr<double>();
+  d.N = static_cast<int32_t>(x.size(0));
+  d.C = static_cast<int32_t>(C);
+  d.h = static_cast<int32_t>(x.size(2));
+  d.w = static_cast<int32_t>(x.size(3));
+  d.dtype = x.scalar_type() == at::kFloat ? DCFP_F32 : DCFP_BF16;
+  d.relu = relu ? 1 : 0;
+  return d;
+}
+
+int64_t bn_scratch_bytes(int64_t C) { return static_cast<int64_t>(dcfp_bn_scratch_bytes(static_cast<int>(C))); }
+
+bool bn_supported(int64_t N, int64_t C, int64_t h, int64_t w, bool bf16) {
+  return dcfp_bn_supported(static_cast<int>(N), static_cast<int>(C), static_cast<int>(h), static_cast<int>(w), bf16 ? DCFP_BF16 : DCFP_F32) != 0;
+}
+
+// -> (y, mean, invstd); sums: the zeroed scratch (fp64 tensor of >= bn_scratch_bytes(C) bytes)
+std::tuple<Tensor, Tensor, Tensor> bn_forward(const Tensor& x, const Tensor& gamma, const Tensor& beta,
+                                              const optional<Tensor>& running_mean, const optional<Tensor>& running_var,
+                                              Tensor sums, double momentum, double eps, bool relu, int64_t phases) {
+  Tensor y = phases == 1 ? at::empty({0}, x.options()) : at::empty_like(x, x.options(), at::MemoryFormat::ChannelsLast);
+  Tensor mean = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
+  Tensor invstd = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
+  dcfp_bn_desc d = bn_desc(x, gamma, beta, mean, invstd, sums, relu);
+  d.phases = static_cast<int32_t>(phases);
+  d.y = phases == 1 ? const_cast<void*>(d.x) : y.data_ptr();  // phase 1 writes no y (validation wants a non-null pointer)
+  TORCH_CHECK(running_mean.has_value() == running_var.has_value(), "dcfp::bn_forward: running_mean / running_var must come together");
+  if (running_mean.has_value()) {
+    d.running_mean = const_cast<float*>(chan_f32(*running_mean, x.size(1), "running_mean"));
+    d.running_var = const_cast<float*>(chan_f32(*running_var, x.size(1), "running_var"));
+  }
+  d.momentum = static_cast<float>(momentum);
+  d.eps = static_cast<float>(eps);
+  c10::cuda::CUDAGuard guard(x.device());
+  check_rc(dcfp_bn_forward(&d, cur_stream()), "bn_forward");
+  return {y, mean, invstd};
+}
+
+// -> (dx or an empty tensor, dgamma, dbeta); S1/S2: fp64 [K,C] class rows (+=); sums: the zeroed scratch
+std::tuple<Tensor, Tensor, Tensor> bn_backward(const Tensor& x, const Tensor& dy, const Tensor& gamma, const Tensor& beta,
+                                               const Tensor& mean, const Tensor& invstd, const optional<Tensor>& keys, Tensor S1,
+                                               Tensor S2, int64_t K, Tensor sums, bool relu, bool need_dx, int64_t phases) {
+  dcfp_bn_desc d = bn_desc(x, gamma, beta, mean, invstd, sums, relu);
+  d.phases = static_cast<int32_t>(phases);
+  if (phases == 1) need_dx = false;  // reduction pass only: no outputs besides sums / S1 / S2
+  require_cuda(dy, "dy");
+  TORCH_CHECK(dy.sizes() == x.sizes() && dy.scalar_type() == x.scalar_type() && dy.is_contiguous(at::MemoryFormat::ChannelsLast),
+              "dcfp::bn_backward: dy must match x (shape, dtype, channels_last)");
+  d.dy = dy.data_ptr();
+  // reuse the K1 descriptor checks for keys / S1 / S2
+  const dcfp_layer_desc L = make_desc(x, dy, invstd, mean, keys, S1, S2, K, DCFP_AFFINE_INVSTD_MEAN);
+  d.keys = L.keys;
+  d.S1 = L.S1;
+  d.S2 = L.S2;
+  d.K = static_cast<int32_t>(K);
+  d.ld = L.ld;
+  Tensor dx = need_dx ? at::empty_like(x, x.options(), at::MemoryFormat::ChannelsLast) : at::empty({0}, x.options());
+  Tensor dgamma = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
+  Tensor dbeta = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
+  d.dx = need_dx ? dx.data_ptr() : nullptr;
+  d.dgamma = dgamma.data_ptr<float>();
+  d.dbeta = dbeta.data_ptr<float>();
+  c10::cuda::CUDAGuard guard(x.device());
+  check_rc(dcfp_bn_backward(&d, cur_stream()), "bn_backward");
+  return {dx, dgamma, dbeta};
+}
+
 int64_t launch_count(bool reset) { return dcfp_launch_count(reset ? 1 : 0); }
 int64_t abi_version() { return dcfp_abi_version(); }
 
@@ -390,6 +479,14 @@ TORCH_LIBRARY(dcfp, m) {
   m.def("bias_comp(Tensor W, Tensor act) -> Tensor", &bias_comp);
   m.def("class_balance_weights(Tensor label, int K, Tensor? sample_class, int mode, float beta, int ignore_label) -> (Tensor, Tensor)",
         &class_balance_weights);
+  m.def("bn_supported(int N, int C, int h, int w, bool bf16) -> bool", &bn_supported);
+  m.def("bn_scratch_bytes(int C) -> int", &bn_scratch_bytes);
+  m.def("bn_forward(Tensor x, Tensor gamma, Tensor beta, Tensor(a!)? running_mean, Tensor(b!)? running_var, Tensor(c!) sums, float momentum, "
+        "float eps, bool relu, int phases=0) -> (Tensor, Tensor, Tensor)",
+        &bn_forward);
+  m.def("bn_backward(Tensor x, Tensor dy, Tensor gamma, Tensor beta, Tensor mean, Tensor invstd, Tensor? keys, Tensor(a!) S1, "
+        "Tensor(b!) S2, int K, Tensor(c!) sums, bool relu, bool need_dx, int phases=0) -> (Tensor, Tensor, Tensor)",
+        &bn_backward);
   m.def("launch_count(bool reset) -> int", &launch_count);
   m.def("abi_version() -> int", &abi_version);
 }

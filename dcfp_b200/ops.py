@@ -101,6 +101,38 @@ def class_balance_weights(label, K, sample_class=None, mode=2, beta=0.9999, igno
     return load().class_balance_weights(label, int(K), sample_class, int(mode), float(beta), int(ignore_label))
 
 
+# ---- f1: fused BatchNorm2d (+ReLU) with the class-keyed sums in its backward ----------------------
+def bn_supported(x):
+    """True when the fused BN kernels take this feature map (channels_last fp32 / bf16, 16-byte channel vectors,
+    at least 64 pixels); anything else stays with torch's BN and the hook path."""
+    if x.dim() != 4 or x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda:
+        return False
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        return False
+    return bool(load().bn_supported(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype == torch.bfloat16))
+
+
+def bn_scratch_elems(C):
+    """fp64 elements of the zeroed scratch one fused BN call (forward or backward) needs for C channels."""
+    return (int(load().bn_scratch_bytes(int(C))) + 7) // 8
+
+
+def bn_scratch(C, device):
+    return torch.zeros(bn_scratch_elems(C), dtype=torch.float64, device=device)
+
+
+def bn_forward(x, gamma, beta, running_mean, running_var, sums, momentum, eps, relu, phases=0):
+    """-> (y, mean, invstd).  sums: zeroed scratch (bn_scratch).  phases: 0 = whole call; 1 = statistics pass only
+    (mean, invstd, running statistics; y is empty); 2 = normalise pass only (after a phases=1 call on the same scratch)."""
+    return load().bn_forward(x, gamma, beta, running_mean, running_var, sums, float(momentum), float(eps), bool(relu), int(phases))
+
+
+def bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, K, sums, relu, need_dx=True, phases=0):
+    """-> (dx | empty, dgamma, dbeta); S1[k,c] += sum dz*xhat, S2 += (dz*xhat)^2 over the pixels of class k.
+    phases: 0 = whole call; 1 = reduction pass only (sums, S1, S2); 2 = dx pass only (after a phases=1 call)."""
+    return load().bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, int(K), sums, bool(relu), bool(need_dx), int(phases))
+
+
 # ---- K2 ----------------------------------------------------------------------------------------
 def r_pair(r):
     """(float32(r), float32(1 - r)) exactly as `eic*r + g*(1-r)` sees them (dcfp_pruner.py:20)."""

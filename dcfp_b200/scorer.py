@@ -34,6 +34,74 @@ from . import ops
 MAX_RESOLUTIONS = 16
 
 
+class _FusedBN(torch.autograd.Function):
+    """Training-mode BatchNorm2d (+ the in-place ReLU that follows it) on the fused sm_100a kernels (SURVEY 8 f1,
+    csrc/bn_fused.cu).  Replaces nn.BatchNorm2d -> nn.ReLU(inplace=True) of the reference nets
+    (networks/backbone/resnet.py:26-56, networks/tools/aspp.py:15-24) for the duration of a scoring pass.  The
+    backward reads (x, dy) ONCE for everything that is a sum -- the class rows S1/S2 of the scorer's arena, dgamma
+    (their row sum: the reference's bn.weight.grad, pruners/dcfp_pruner.py:18) and dbeta -- and once more for dx."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer, relu):
+        sc, module = layer.scorer, layer.module
+        factor = 0.0
+        rm = rv = None
+        if module.track_running_stats and module.running_mean is not None:
+            rm, rv = module.running_mean, module.running_var
+            if module.momentum is None:  # cumulative moving average
+                module.num_batches_tracked.add_(1)
+                factor = 1.0 / float(module.num_batches_tracked)
+            else:
+                factor = module.momentum
+                if sc.track_counters:
+                    module.num_batches_tracked.add_(1)
+        sums_f, sums_b = sc._bn_scratch(layer)
+        nb = x.numel() * x.element_size()
+        if sc.timing:  # the two passes timed apart
+            t = sc._t_begin()
+            _, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, phases=1)
+            sc._t_end(t, "bn_fwd_stats", nb)
+            t = sc._t_begin()
+            y, _, _ = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, phases=2)
+            sc._t_end(t, "bn_fwd_apply", 2 * nb)
+        else:
+            y, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu)
+        ctx.save_for_backward(x, weight, bias, mean, invstd)
+        ctx.layer, ctx.relu, ctx.sums_b = layer, relu, sums_b
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, weight, bias, mean, invstd = ctx.saved_tensors
+        layer = ctx.layer
+        sc = layer.scorer
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        need_dx = ctx.needs_input_grad[0]
+        keys = sc._keys_for(x.shape[2], x.shape[3])
+        nb = x.numel() * x.element_size()
+        if sc.timing:  # the two passes timed apart: B1 (class-keyed reduction) is the path's dominant kernel
+            t = sc._t_begin()
+            ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b, ctx.relu, need_dx, phases=1)
+            sc._t_end(t, "bn_bwd_reduce", 2 * nb + keys.numel())
+            t = sc._t_begin()
+            dx, dgamma, dbeta = ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b,
+                                                ctx.relu, need_dx, phases=2)
+            sc._t_end(t, "bn_bwd_dx", 3 * nb if need_dx else 0)
+        else:
+            dx, dgamma, dbeta = ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b,
+                                                ctx.relu, need_dx)
+        sc.k1_bytes += 2 * nb + keys.numel()
+        return (dx if need_dx else None), dgamma, dbeta, None, None
+
+
+class _FusedLayer:
+    __slots__ = ("scorer", "name", "module", "S1", "S2", "index")
+
+    def __init__(self, scorer, name, module, S1, S2, index):
+        self.scorer, self.name, self.module, self.S1, self.S2, self.index = scorer, name, module, S1, S2, index
+
+
 def scored_layers(model):
     """BN layers the reference scores (dcfp_pruner.py:11-13), in `named_modules` order."""
     ignore = getattr(model, "ignore_prune_layer", [])
@@ -65,7 +133,7 @@ def average_over_ranks(t, group=None):
 
 class ClassStatsScorer:
     def __init__(self, model, num_classes, mode="bwd", r=0.999, process_group=None, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False):
+                 timing=False, fused=True, track_counters=True):
         ops.require_gpu()
         assert mode in ("bwd", "fwd")
         self.model, self.K, self.mode, self.r = model, int(num_classes), mode, r
@@ -73,6 +141,18 @@ class ClassStatsScorer:
         self.layers = scored_layers(model)
         if not self.layers:
             raise ValueError("model has no scored BatchNorm layers")
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1 and \
+                any(isinstance(m, nn.SyncBatchNorm) for _, m in self.layers):
+            # engine.py:65 converts to SyncBN: those layers normalise with statistics of the GLOBAL batch, which neither
+            # the hook path (rank-local mean / invstd) nor the fused kernels reproduce.  Refuse instead of scoring with
+            # the wrong xhat (micro-batches are fixed by global index instead).
+            raise RuntimeError("ClassStatsScorer: the model contains SyncBatchNorm layers and torch.distributed runs with world "
+                               "size > 1; score a plain BatchNorm2d replica per rank (nn.SyncBatchNorm is not supported)")
+        # fused: BN(+ReLU) forward / backward on the library's own kernels, the class-keyed sums coming out of the BN
+        # backward itself (bwd mode, channels_last training-mode layers; everything else keeps torch's BN + the hooks)
+        self.fused = bool(fused) and mode == "bwd"
+        self.track_counters = bool(track_counters)
         self.device = self.layers[0][1].weight.device
         if self.device.type != "cuda":
             raise RuntimeError("ClassStatsScorer: the model must live on a CUDA device (no CPU fallback)")
@@ -108,11 +188,28 @@ class ClassStatsScorer:
         self.timing = timing
         self.k1_events = []  # (start, end, algorithmic bytes) per K1 launch when timing
         self.k1_bytes = 0
+        self.phase_events = []  # (kind, start, end, algorithmic bytes) of the fused BN passes when timing
+        # fused BN: one scratch per layer and direction (striped fp64 partial sums + coefficient vectors, csrc/bn_common.cuh),
+        # all of them in one flat buffer zeroed once per step
+        self._bn_ws = None
+        if self.fused:
+            self._bn_ws_off = [0]
+            for c in sizes:
+                self._bn_ws_off.append(self._bn_ws_off[-1] + ops.bn_scratch_elems(c))
+            self._bn_ws = torch.zeros(2 * self._bn_ws_off[-1], dtype=torch.float64, device=self.device)
+        self._fused_layers = {n: _FusedLayer(self, n, m, self._views[n][0], self._views[n][1], i)
+                              for i, (n, m) in enumerate(self.layers)} if self.fused else {}
+        self._fused_calls = {}
+        self._relu_after = {}  # bn name -> True once an in-place nn.ReLU was seen consuming that BN's output
+        self._patched = []
+        self.fused_layer_calls = 0
 
     # ------------------------------------------------------------------ hooks
     def attach(self):
         for name, module in self.layers:
             self._handles.append(module.register_forward_hook(self._make_hook(name)))
+        if self.fused:
+            self._patch_modules()
         return self
 
     def detach(self):
@@ -120,11 +217,90 @@ class ClassStatsScorer:
             h.remove()
         self._handles = []
         self._pending, self._pending_fwd, self._pending_bytes = [], [], 0
+        for module in self._patched:  # drop the instance-level forward: the class's own forward is back
+            module.__dict__.pop("forward", None)
+        self._patched = []
+
+    # ------------------------------------------------------------------ fused BN (+ReLU)
+    def _patch_modules(self):
+        """Instance-level `forward` overrides, removed by detach():
+          * every scored BatchNorm2d runs _FusedBN when its input is eligible (training mode, labels set, channels_last
+            fp32 / bf16, >= 64 pixels), else its own forward (then the forward hook / K1 path scores it);
+          * every nn.ReLU returns its input untouched when that input is a fused BN output that already went through
+            the ReLU, and otherwise LEARNS: an in-place ReLU applied to a fused BN's output marks that BN as
+            "followed by ReLU", so from the next step on the two are one kernel.  The first step of a pass therefore
+            runs BN and ReLU apart -- with bit-identical results (same fma, same gate).  bn3 + residual add + ReLU of
+            a bottleneck stays unfused: the ReLU's input there is the sum, not a BN output."""
+        sc = self
+        for name, module in self.layers:
+            if "forward" in module.__dict__ or not isinstance(module, nn.BatchNorm2d) or module.weight is None:
+                continue
+            layer = self._fused_layers[name]
+
+            def bn_forward(x, _m=module, _layer=layer, _name=name):
+                if not sc._eligible(_m, x):
+                    return type(_m).forward(_m, x)
+                relu = sc._relu_after.get(_name, False)
+                y = _FusedBN.apply(x, _m.weight, _m.bias, _layer, relu)
+                y._dcfp_bn = (_name, relu)
+                sc.fused_layer_calls += 1
+                return y
+
+            module.forward = bn_forward
+            self._patched.append(module)
+        for module in self.model.modules():
+            if isinstance(module, nn.ReLU) and "forward" not in module.__dict__:
+                def relu_forward(inp, _m=module):
+                    tag = getattr(inp, "_dcfp_bn", None)
+                    if tag is not None:
+                        if tag[1]:
+                            return inp  # the fused BN kernel already applied the ReLU
+                        if _m.inplace:
+                            sc._relu_after[tag[0]] = True
+                    return type(_m).forward(_m, inp)
+
+                module.forward = relu_forward
+                self._patched.append(module)
+
+    def _eligible(self, module, x):
+        if self._labels is None or not torch.is_grad_enabled() or not (module.training or module.running_mean is None):
+            return False
+        if module.weight.dtype != torch.float32 or not (x.requires_grad or module.weight.requires_grad):
+            return False
+        return ops.bn_supported(x)
+
+    def _bn_scratch(self, layer):
+        """(forward, backward) scratch of this call: slices of the per-step workspace, or fresh buffers when the module
+        runs more than once per step (shared modules)."""
+        n = self._fused_calls.get(layer.name, 0)
+        self._fused_calls[layer.name] = n + 1
+        if n > 0:
+            C = layer.module.weight.numel()
+            return ops.bn_scratch(C, self.device), ops.bn_scratch(C, self.device)
+        a, b, half = self._bn_ws_off[layer.index], self._bn_ws_off[layer.index + 1], self._bn_ws_off[-1]
+        return self._bn_ws[a:b], self._bn_ws[half + a:half + b]
+
+    def _t_begin(self):
+        if not self.timing:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _t_end(self, e0, kind, nbytes):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.phase_events.append((kind, e0, e1, nbytes))
 
     def set_labels(self, labels):
         """labels of the micro-batch about to run: [N, H0, W0] uint8 / int32 / int64 on the device."""
         self._labels = labels.contiguous()
         self._keys = {}
+        if self._bn_ws is not None:
+            self._bn_ws.zero_()
+            self._fused_calls = {}
 
     def _keys_for(self, h, w):
         key = (h, w)
@@ -202,7 +378,7 @@ class ClassStatsScorer:
         S1, S2 = self._views[name]
 
         def hook(module, inputs, output):
-            if self._labels is None:
+            if self._labels is None or getattr(output, "_dcfp_bn", None) is not None:  # fused layers score themselves
                 return
             x = inputs[0]
             if self.mode == "fwd":
@@ -319,6 +495,15 @@ class ClassStatsScorer:
         ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.k1_events)
         return ms, sum(b for _, _, b in self.k1_events), len(self.k1_events)
 
+    def phase_times(self):
+        """{kind: (ms, algorithmic bytes, calls)} of the fused BN passes (timing=True) -- call after a synchronize.
+        kinds: bn_fwd_stats (F1), bn_fwd_apply (F2), bn_bwd_reduce (B1: the class-keyed reduction), bn_bwd_dx (B2)."""
+        out = {}
+        for kind, e0, e1, nb in self.phase_events:
+            ms, b, n = out.get(kind, (0.0, 0, 0))
+            out[kind] = (ms + e0.elapsed_time(e1), b + nb, n + 1)
+        return out
+
 
 class CalibrationRun:
     """Step-wise driver of the scoring pass (bench.py times `step`; `score_calibration_set` loops it).
@@ -331,7 +516,7 @@ class CalibrationRun:
     all-reduce before the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
 
     def __init__(self, model, num_classes, r=0.999, mode="bwd", restore_bn_stats=True, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, process_group=None, seed=None, scores_only=False):
+                 timing=False, process_group=None, seed=None, scores_only=False, fused=True):
         ops.require_gpu()
         self.model = model
         self.seed = seed
@@ -347,8 +532,10 @@ class CalibrationRun:
                     p_.requires_grad_(False)
                     self._frozen.append(p_)
         self.device = next(model.parameters()).device
+        # restore_bn_stats puts num_batches_tracked back at close(): the fused layers then skip its per-layer increment
         self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
-                                       keep_totals=keep_totals, timing=timing).attach()
+                                       keep_totals=keep_totals, timing=timing, fused=fused,
+                                       track_counters=not restore_bn_stats).attach()
         self._saved = None
         if restore_bn_stats:  # train-mode BN updates its running statistics: snapshot them (a few fused launches)
             bns = [m for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.running_mean is not None]
@@ -401,7 +588,7 @@ class CalibrationRun:
 
 
 def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, flush_bytes=1 << 30,
-                          return_class_stats=False, seed=0, scores_only=False, channels_last=True):
+                          return_class_stats=False, seed=0, scores_only=False, channels_last=True, fused=True):
     """Public end-to-end call: HOST images [n,3,H,W] / labels [n,H,W] -> EIC scores on the host.
 
     Every step copies its micro-batch host->device from pinned memory and reads the step's loss back;
@@ -425,7 +612,7 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     rank = torch.distributed.get_rank() if dist_on else 0
     plan = shard_plan(images.shape[0], micro_batch, world, rank)
     run = CalibrationRun(model, num_classes, r=r, restore_bn_stats=restore_bn_stats, flush_bytes=flush_bytes,
-                         keep_totals=return_class_stats, seed=seed, scores_only=scores_only)
+                         keep_totals=return_class_stats, seed=seed, scores_only=scores_only, fused=fused)
     h2d = d2h = 0
     losses = torch.empty(max(len(plan), 1), dtype=torch.float32).pin_memory()
     launches0 = ops.launch_count()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DCFP_ABI_VERSION 2
+#define DCFP_ABI_VERSION 3
 
 /* element types of feature maps / weights */
 #define DCFP_F32 0
@@ -46,6 +46,9 @@ extern "C" {
 #define DCFP_EINVAL (-1)      /* bad argument (null pointer, non-positive extent, unknown enum) */
 #define DCFP_EUNSUPPORTED (-2) /* valid but not implemented combination */
 #define DCFP_ETOOBIG (-3)     /* exceeds a documented limit (K > 255, too many layers, ...) */
+
+/* dcfp_layer_desc.hints */
+#define DCFP_HINT_KEEP_L2 1 /* another pass re-reads this map soon: load with normal L2 priority instead of evict-first */
 
 #define DCFP_MAX_CLASSES 255
 #define DCFP_MAX_GROUP_LAYERS 160
@@ -92,7 +95,7 @@ typedef struct dcfp_layer_desc {
   int32_t layout; /* DCFP_NCHW | DCFP_NHWC */
   int32_t ld;     /* row stride of S1/S2 in elements (0 -> C): lets all layers share one [K, sum C] arena */
   int32_t affine_mode; /* DCFP_AFFINE_SCALE_SHIFT | DCFP_AFFINE_INVSTD_MEAN */
-  int32_t reserved;    /* must be 0 */
+  int32_t hints;       /* 0, or DCFP_HINT_* bits (was `reserved`, must-be-0, in ABI v2) */
 } dcfp_layer_desc;
 
 /* ---- K1: label-keyed segmented reduction over conv/BN feature maps -------------------------
@@ -168,6 +171,54 @@ int dcfp_bias_comp(const float* W, int O, int I, int khw, const float* act, floa
 int dcfp_class_balance_weights(const void* label, int label_dtype, int N, int H, int W, int K, int ignore_label,
                                const int32_t* sample_class, int mode, double beta, int64_t* class_num, double* weight,
                                void* stream);
+
+/* ---- f1: training-mode BatchNorm2d (+ in-place ReLU) whose backward yields the class-keyed sums ---------------
+ * Replaces nn.BatchNorm2d followed by nn.ReLU(inplace=True) as the reference nets use them
+ * (networks/backbone/resnet.py:26-56, networks/tools/aspp.py:15-24) and, inside loss.backward()
+ * (train.py:265), autograd's ReLU + batch-norm backward whose bn.weight.grad pruners/dcfp_pruner.py:18
+ * reads.  channels_last maps only (dcfp_bn_supported tells; anything else stays with torch's BN and the
+ * hook path of dcfp_class_stats).
+ *   forward : mean/var over the N*h*w pixels (fp64 across CTAs), y = [relu](fma(x, gamma*invstd,
+ *             beta - mean*gamma*invstd)); mean, invstd written for the backward; running statistics
+ *             updated with `momentum` (the exponential_average_factor; unbiased variance), if given.
+ *   backward: dz = dy where the forward output was > 0 (relu) else dy;  S1[k][c] += sum_{p in class k}
+ *             dz*xhat, S2 += (dz*xhat)^2 -- the SAME class rows dcfp_class_stats' backward functor fills,
+ *             so sum_k S1 == dgamma;  dgamma, dbeta (fp32 [C]);  dx = gamma*invstd*(dz - dbeta/M -
+ *             xhat*dgamma/M) unless dx == NULL.  (x, dy) are read once for all sums, once more for dx.
+ * `scratch`: caller-provided device buffer of dcfp_bn_scratch_bytes(C) bytes, 8-byte aligned, ZERO on entry
+ * (fp64 partial sums striped against same-address atomic contention + the coefficient vectors the reduction
+ * pass leaves for the element-wise pass + a ticket counter); one scratch per call in flight.            */
+typedef struct dcfp_bn_desc {
+  const void* x;         /* [N,h,w,C] (channels_last), dtype `dtype` */
+  void* y;               /* forward out, same shape */
+  const void* dy;        /* backward in */
+  void* dx;              /* backward out, or NULL */
+  const float* gamma;    /* [C] */
+  const float* beta;     /* [C] */
+  float* mean;           /* [C] forward: written; backward: read */
+  float* invstd;         /* [C] */
+  float* running_mean;   /* [C] or NULL (forward) */
+  float* running_var;    /* [C] or NULL */
+  void* scratch;         /* dcfp_bn_scratch_bytes(C) bytes, zero on entry */
+  const uint8_t* keys;   /* backward: [N,h,w] class keys, or NULL (K == 1) */
+  double* S1;            /* backward: [K, ld] class rows */
+  double* S2;
+  float* dgamma;         /* backward out [C] */
+  float* dbeta;          /* backward out [C] */
+  int32_t N, C, h, w;
+  int32_t dtype;         /* DCFP_F32 | DCFP_BF16 */
+  int32_t relu;          /* 1: the BN output goes through ReLU (fused) */
+  int32_t K, ld;         /* backward: class rows, row stride of S1/S2 (0 -> C) */
+  float eps, momentum;
+  int32_t phases;        /* 0: the whole call; 1: only the reduction pass (sums, statistics / gradients of gamma and
+                            beta [+ S1/S2]); 2: only the element-wise pass (needs the scratch a phase-1 call left) --
+                            lets a caller time the two apart */
+  int32_t reserved;      /* must be 0 */
+} dcfp_bn_desc;
+int dcfp_bn_supported(int N, int C, int h, int w, int dtype);
+size_t dcfp_bn_scratch_bytes(int C);
+int dcfp_bn_forward(const dcfp_bn_desc* desc_host, void* stream);
+int dcfp_bn_backward(const dcfp_bn_desc* desc_host, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------- */
 const char* dcfp_last_error(void);

@@ -1,0 +1,185 @@
+"""f1 parity: the fused BatchNorm2d(+ReLU) forward / backward kernels (torch.ops.dcfp.bn_* -> C ABI) against
+(a) torch autograd of relu(batch_norm(x)) in fp64 on the same inputs and (b) the K1 oracle for the class rows.
+
+Tolerances, written against the absolute mass of what is summed (fp32 inside a warp, fp64 across CTAs):
+    y, dx        |a - b| <= 1e-5 * (|b| + rms(b))
+    mean, invstd |a - b| <= 1e-6 * (|b| + rms(b))       (fp64 sums, one fp32 rounding)
+    dgamma/dbeta |a - b| <= 1e-5 * sum|terms|
+    S1 rows      |a - b| <= 1e-5 * sum|v|,   S2 rows  1e-5 relative
+"""
+import pytest
+import torch
+
+from oracle import bn_ref
+from oracle import class_stats_ref as ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _labels(n, h0, w0, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    coarse = torch.randint(0, K, (n, max(h0 // 16, 1), max(w0 // 16, 1)), generator=g)
+    lab = torch.nn.functional.interpolate(coarse[:, None].float(), size=(h0, w0), mode="nearest")[:, 0].long()
+    lab[torch.rand(n, h0, w0, generator=g) < 0.03] = 255
+    return lab
+
+
+def _close(a, b, rtol, what):
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = b.pow(2).mean().sqrt()
+    err = (a - b).abs()
+    bound = rtol * (b.abs() + scale)
+    assert (err <= bound).all(), "%s: max err/bound %.3g (rms of the reference %.3g)" % (what, (err / bound).max(), scale)
+
+
+def _inputs(N, C, h, w, seed, offset=0.0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(N, C, h, w, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g)) + offset * torch.randn(1, C, 1, 1, generator=g))
+    dy = torch.randn(N, C, h, w, generator=g) * 1e-3
+    gamma = 0.5 + torch.rand(C, generator=g)
+    gamma[::7] *= -1  # negative gammas exist after training; the gate must follow gamma * xhat + beta
+    beta = 0.3 * torch.randn(C, generator=g)
+    cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)
+    return cl(x), cl(dy), gamma.to(DEV), beta.to(DEV)
+
+
+SHAPES = [
+    # N, C, h, w, K
+    (2, 256, 64, 128, 19),   # the dominant c2 shape
+    (2, 64, 128, 256, 19),   # pixel-pair rows
+    (2, 1024, 32, 64, 19),   # 8 slabs
+    (2, 2048, 16, 32, 150),  # 2 slab groups, two column blocks in the streaming kernels
+    (2, 48, 64, 64, 171),    # partial slab (decoder.conv1 of DeepLabV3+)
+    (3, 96, 40, 52, 150),    # ragged rows
+    (2, 512, 6, 8, 19),      # 96 pixels: the smallest map the fused path takes
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("relu", [True, False])
+def test_forward_matches_fp64_batch_norm(native, shape, relu):
+    from dcfp_b200 import ops
+    N, C, h, w, K = shape
+    x, _, gamma, beta = _inputs(N, C, h, w, seed=C + h, offset=1.0)
+    assert ops.bn_supported(x)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    sums = ops.bn_scratch(C, DEV)
+    y, mean, invstd = ops.bn_forward(x, gamma, beta, rm, rv, sums, 0.1, 1e-5, relu)
+    torch.cuda.synchronize()
+    assert y.is_contiguous(memory_format=torch.channels_last) and y.shape == x.shape
+    xd = x.double()
+    rm64, rv64 = torch.zeros(C, dtype=torch.float64, device=DEV), torch.ones(C, dtype=torch.float64, device=DEV)
+    y64 = torch.nn.functional.batch_norm(xd, rm64, rv64, gamma.double(), beta.double(), True, 0.1, 1e-5)
+    if relu:
+        y64 = torch.relu(y64)
+    var, mu = torch.var_mean(xd, dim=(0, 2, 3), unbiased=False)
+    _close(mean, mu, 1e-6, "mean")
+    _close(invstd, torch.rsqrt(var + 1e-5), 1e-6, "invstd")
+    _close(y, y64, 1e-5, "y")
+    _close(rm, rm64, 1e-6, "running_mean")
+    _close(rv, rv64, 1e-6, "running_var")
+    # the factored oracle (oracle/bn_ref.py) is the same function
+    yo, mo, io = bn_ref.bn_relu_forward(xd, gamma.double(), beta.double(), 1e-5, relu)
+    _close(y, yo, 1e-5, "y vs oracle")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("relu", [True, False])
+def test_backward_matches_fp64_autograd_and_class_rows(native, shape, relu):
+    from dcfp_b200 import ops
+    N, C, h, w, K = shape
+    x, dy, gamma, beta = _inputs(N, C, h, w, seed=3 * C + w)
+    label = _labels(N, h * 4, w * 4, K, seed=h)
+    R = K + 1  # row K: pixels whose label is outside [0, K)
+    keys = ops.label_keys(label.to(DEV), h, w, K)
+    sums = ops.bn_scratch(C, DEV)
+    y, mean, invstd = ops.bn_forward(x, gamma, beta, None, None, sums, 0.1, 1e-5, relu)
+    ld = C + 24  # a column slice of a wider arena, with guard columns on both sides
+    arena = torch.zeros(2, R, ld, dtype=torch.float64, device=DEV)
+    S1, S2 = arena[0][:, 8:8 + C], arena[1][:, 8:8 + C]
+    sums_b = ops.bn_scratch(C, DEV)
+    dx, dgamma, dbeta = ops.bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, R, sums_b, relu, True)
+    torch.cuda.synchronize()
+    # (a) fp64 autograd of the same function on the same inputs
+    x64 = x.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    y64 = torch.nn.functional.batch_norm(x64, None, None, g64, b64, True, 0.1, 1e-5)
+    if relu:
+        y64 = torch.relu(y64)
+    y64.backward(dy.double())
+    _close(y, y64.detach(), 1e-5, "y")
+    # the gate of a pixel whose pre-activation rounds to the other side of 0 may differ between fp32 and fp64: such
+    # pixels have |z| < 1e-6 and are a ~1e-7 fraction; compare dx where the two gates agree
+    if relu:
+        agree = ((y > 0) == (y64.detach() > 0))
+        assert agree.float().mean() > 1 - 1e-5
+    else:
+        agree = torch.ones_like(y, dtype=torch.bool)
+    ex = (dx.double() - x64.grad).abs()
+    bound = 1e-5 * (x64.grad.abs() + x64.grad.pow(2).mean().sqrt())
+    assert (ex[agree] <= bound[agree]).all(), "dx: max err %.3g" % ex[agree].max()
+    with torch.no_grad():
+        xhat = (x.double() - mean.double().view(1, -1, 1, 1)) * invstd.double().view(1, -1, 1, 1)
+        dz = dy.double() * (y > 0) if relu else dy.double()
+        v = dz * xhat
+        mass_g = v.abs().sum(dim=(0, 2, 3))
+        mass_b = dz.abs().sum(dim=(0, 2, 3))
+    assert ((dgamma.double() - g64.grad).abs() <= 1e-5 * mass_g + 1e-30).all(), "dgamma"
+    assert ((dbeta.double() - b64.grad).abs() <= 1e-5 * mass_b + 1e-30).all(), "dbeta"
+    # (b) class rows vs the K1 oracle on v = dz * xhat (values as the kernel sees them), rows sum to dgamma
+    rc, r1, r2 = ref.class_stats(v.cpu(), label, K)
+    o1, o2 = ref.outside_stats(v.cpu(), label, K)
+    r1, r2 = torch.cat([r1, o1[None]]), torch.cat([r2, o2[None]])
+    mass = torch.cat([ref.abs_mass(v.cpu(), label, K), ref.outside_stats(v.abs().cpu(), label, K)[0][None]])
+    e1 = (S1.cpu() - r1).abs()
+    assert (e1 <= 1e-5 * mass + 1e-30).all(), "S1 rows: max rel-to-mass %.3g" % (e1 / (mass + 1e-30)).max()
+    e2 = (S2.cpu() - r2).abs()
+    assert (e2 <= 1e-5 * r2 + 1e-30).all(), "S2 rows"
+    assert ((S1.sum(0) - dgamma.double()).abs().cpu() <= 1e-6 * mass_g.cpu() + 1e-30).all(), "row-sum identity: sum_k S1 == dgamma"
+    # guard columns untouched
+    assert float(arena[:, :, :8].abs().sum()) == 0.0 and float(arena[:, :, 8 + C:].abs().sum()) == 0.0
+    # no input gradient wanted: same sums, no dx
+    arena.zero_()
+    sums_b.zero_()
+    dx0, dg0, db0 = ops.bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, R, sums_b, relu, False)
+    assert dx0.numel() == 0
+    _close(dg0, dgamma, 1e-6, "dgamma without dx")
+    _close(db0, dbeta, 1e-6, "dbeta without dx")
+
+
+def test_bf16_forward_backward(native):
+    from dcfp_b200 import ops
+    N, C, h, w, K = 2, 256, 32, 64, 19
+    x, dy, gamma, beta = _inputs(N, C, h, w, seed=5)
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    assert ops.bn_supported(xb)
+    label = _labels(N, h * 8, w * 8, K, seed=1)
+    keys = ops.label_keys(label.to(DEV), h, w, K)
+    sums = ops.bn_scratch(C, DEV)
+    y, mean, invstd = ops.bn_forward(xb, gamma, beta, None, None, sums, 0.1, 1e-5, True)
+    S1 = torch.zeros(K + 1, C, dtype=torch.float64, device=DEV)
+    S2 = torch.zeros_like(S1)
+    sums_b = ops.bn_scratch(C, DEV)
+    dx, dgamma, dbeta = ops.bn_backward(xb, dyb, gamma, beta, mean, invstd, keys, S1, S2, K + 1, sums_b, True, True)
+    x64 = xb.double().requires_grad_(True)
+    g64 = gamma.double().requires_grad_(True)
+    y64 = torch.relu(torch.nn.functional.batch_norm(x64, None, None, g64, beta.double(), True, 0.1, 1e-5))
+    y64.backward(dyb.double())
+    assert y.dtype == torch.bfloat16 and dx.dtype == torch.bfloat16
+    _close(y.float(), y64.detach(), 1e-2, "y bf16")       # one bf16 rounding of the output
+    _close(dx.float(), x64.grad, 1.5e-2, "dx bf16")
+    _close(dgamma, g64.grad, 2e-3, "dgamma bf16")        # gate flips of values that round across 0 in bf16
+    assert ((S1.sum(0) - dgamma.double()).abs() <= 1e-6 * dgamma.abs().max()).all()
+
+
+def test_rejects_unsupported_inputs(native):
+    from dcfp_b200 import ops
+    x = torch.randn(2, 64, 16, 16, device=DEV)  # NCHW
+    assert not ops.bn_supported(x)
+    assert not ops.bn_supported(torch.randn(2, 30, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last))
+    assert not ops.bn_supported(torch.randn(2, 64, 1, 1, device=DEV).contiguous(memory_format=torch.channels_last))
+    g = torch.ones(64, device=DEV)
+    sums = ops.bn_scratch(64, DEV)
+    with pytest.raises(RuntimeError):
+        ops.bn_forward(x, g, g, None, None, sums, 0.1, 1e-5, True)

@@ -36,7 +36,7 @@ def test_class_stats_and_eic_through_ctypes(native):
     assert rc == 0, abi.last_error()
     d = abi.LayerDesc(x=xd.data_ptr(), dy=dyd.data_ptr(), scale=sd.data_ptr(), shift=md.data_ptr(), keys=keys.data_ptr(),
                       S1=S1.data_ptr(), S2=S2.data_ptr(), N=N, C=C, h=h, w=w, K=K, dtype=abi.F32, layout=abi.NCHW, ld=C,
-                      affine_mode=1, reserved=0)
+                      affine_mode=1, hints=0)
     rc = lib.dcfp_class_stats(ctypes.byref(d), sp)
     assert rc == 0, abi.last_error()
     dgamma = torch.empty(C, dtype=torch.float32, device=dev)
