@@ -30,7 +30,8 @@ class BnDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("x", "y", "dy", "dx", "gamma", "beta", "mean", "invstd", "running_mean", "running_var",
                                                "scratch", "keys", "S1", "S2", "dgamma", "dbeta")] + \
                [(n, ctypes.c_int32) for n in ("N", "C", "h", "w", "dtype", "relu", "K", "ld")] + \
-               [("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("phases", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+               [("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("phases", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64)]
 
 
 class GatherDesc(ctypes.Structure):
@@ -67,6 +68,8 @@ def load(path=LIB_PATH):
     lib.dcfp_bn_supported.argtypes = [i32, i32, i32, i32, i32]
     lib.dcfp_bn_scratch_bytes.restype = ctypes.c_size_t
     lib.dcfp_bn_scratch_bytes.argtypes = [i32]
+    lib.dcfp_bn_workspace_bytes.restype = ctypes.c_size_t
+    lib.dcfp_bn_workspace_bytes.argtypes = [i32]
     lib.dcfp_bn_forward.argtypes = [ctypes.POINTER(BnDesc), vp]
     lib.dcfp_bn_backward.argtypes = [ctypes.POINTER(BnDesc), vp]
     lib.dcfp_eic_update.argtypes = [vp, vp, vp, i32, vp, ctypes.c_float, ctypes.c_float, i32, vp]

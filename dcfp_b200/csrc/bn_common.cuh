@@ -13,15 +13,20 @@ namespace dcfp {
 
 constexpr int kBnStripes = 8;
 
-// scratch = double stripes[kBnStripes][2][C] | float coef[5][C] | unsigned counter (+ pad); ZERO on entry
+constexpr int kBnMaxCtas = 512;  // grid-barrier flags of the cooperative kernels (one per CTA; grids are <= #SMs)
+
+// scratch = double stripes[kBnStripes][2][C] | float coef[5][C] | unsigned counter, pad[3] | unsigned flags[kBnMaxCtas];
+// ZERO on entry
 __host__ __device__ inline size_t bn_scratch_bytes(int C) {
-  return static_cast<size_t>(kBnStripes) * 2 * C * sizeof(double) + static_cast<size_t>(5) * C * sizeof(float) + 16;
+  return static_cast<size_t>(kBnStripes) * 2 * C * sizeof(double) + static_cast<size_t>(5) * C * sizeof(float) + 16 +
+         kBnMaxCtas * sizeof(unsigned);
 }
 __host__ __device__ inline double* bn_stripes(void* scratch) { return static_cast<double*>(scratch); }
 __host__ __device__ inline float* bn_coef(void* scratch, int C) {
   return reinterpret_cast<float*>(static_cast<char*>(scratch) + static_cast<size_t>(kBnStripes) * 2 * C * sizeof(double));
 }
 __host__ __device__ inline unsigned* bn_counter(void* scratch, int C) { return reinterpret_cast<unsigned*>(bn_coef(scratch, C) + 5 * C); }
+__host__ __device__ inline unsigned* bn_flags(void* scratch, int C) { return bn_counter(scratch, C) + 4; }
 
 struct BnFinal {
   void* scratch;

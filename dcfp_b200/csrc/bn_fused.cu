@@ -19,8 +19,10 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "bn_common.cuh"
+#include "bn_coop.cuh"
 
 namespace dcfp {
 
@@ -374,6 +376,7 @@ extern "C" int dcfp_bn_supported(int N, int C, int h, int w, int dtype) {
 }
 
 extern "C" size_t dcfp_bn_scratch_bytes(int C) { return C > 0 ? dcfp::bn_scratch_bytes(C) : 0; }
+extern "C" size_t dcfp_bn_workspace_bytes(int C) { return C > 0 ? dcfp::coop_workspace_bytes(C) : 0; }
 
 extern "C" int dcfp_bn_forward(const dcfp_bn_desc* d, void* stream_) {
   using namespace dcfp;
@@ -381,6 +384,14 @@ extern "C" int dcfp_bn_forward(const dcfp_bn_desc* d, void* stream_) {
   const int rc = validate_bn(d, false);
   if (rc) return rc;
   DCFP_REQUIRE(dcfp_bn_supported(d->N, d->C, d->h, d->w, d->dtype), DCFP_EUNSUPPORTED, "bn_forward: map not eligible (see dcfp_bn_supported)");
+  // one cooperative launch (statistics + normalise, the tail of x staying in shared memory) when the caller provides
+  // the workspace and asks for the whole call; the two-launch path otherwise (and for phases-apart timing)
+  static const int coop_off = []() {
+    const char* e = getenv("DCFP_BN_COOP");
+    return e && atoi(e) == 0;
+  }();
+  if (d->workspace != nullptr && d->phases == 0 && !coop_off)
+    return d->dtype == DCFP_F32 ? coop_forward<float>(d, final_args(d), stream) : coop_forward<__nv_bfloat16>(d, final_args(d), stream);
   return d->dtype == DCFP_F32 ? forward_t<float>(d, stream) : forward_t<__nv_bfloat16>(d, stream);
 }
 

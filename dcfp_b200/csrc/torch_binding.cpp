@@ -395,6 +395,7 @@ dcfp_bn_desc bn_desc(const Tensor& x, const Tensor& gamma, const Tensor& beta, c
   return d;
 }
 
+int64_t bn_workspace_bytes(int64_t C) { return static_cast<int64_t>(dcfp_bn_workspace_bytes(static_cast<int>(C))); }
 int64_t bn_scratch_bytes(int64_t C) { return static_cast<int64_t>(dcfp_bn_scratch_bytes(static_cast<int>(C))); }
 
 bool bn_supported(int64_t N, int64_t C, int64_t h, int64_t w, bool bf16) {
@@ -404,7 +405,8 @@ bool bn_supported(int64_t N, int64_t C, int64_t h, int64_t w, bool bf16) {
 // -> (y, mean, invstd); sums: the zeroed scratch (fp64 tensor of >= bn_scratch_bytes(C) bytes)
 std::tuple<Tensor, Tensor, Tensor> bn_forward(const Tensor& x, const Tensor& gamma, const Tensor& beta,
                                               const optional<Tensor>& running_mean, const optional<Tensor>& running_var,
-                                              Tensor sums, double momentum, double eps, bool relu, int64_t phases) {
+                                              Tensor sums, double momentum, double eps, bool relu, int64_t phases,
+                                              const optional<Tensor>& workspace) {
   Tensor y = phases == 1 ? at::empty({0}, x.options()) : at::empty_like(x, x.options(), at::MemoryFormat::ChannelsLast);
   Tensor mean = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
   Tensor invstd = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
@@ -418,6 +420,12 @@ std::tuple<Tensor, Tensor, Tensor> bn_forward(const Tensor& x, const Tensor& gam
   }
   d.momentum = static_cast<float>(momentum);
   d.eps = static_cast<float>(eps);
+  if (workspace.has_value()) {
+    require_cuda(*workspace, "workspace");
+    TORCH_CHECK(workspace->is_contiguous(), "dcfp::bn_forward: workspace must be contiguous");
+    d.workspace = workspace->data_ptr();
+    d.workspace_bytes = static_cast<int64_t>(workspace->numel() * workspace->element_size());
+  }
   c10::cuda::CUDAGuard guard(x.device());
   check_rc(dcfp_bn_forward(&d, cur_stream()), "bn_forward");
   return {y, mean, invstd};
@@ -481,8 +489,9 @@ TORCH_LIBRARY(dcfp, m) {
         &class_balance_weights);
   m.def("bn_supported(int N, int C, int h, int w, bool bf16) -> bool", &bn_supported);
   m.def("bn_scratch_bytes(int C) -> int", &bn_scratch_bytes);
+  m.def("bn_workspace_bytes(int C) -> int", &bn_workspace_bytes);
   m.def("bn_forward(Tensor x, Tensor gamma, Tensor beta, Tensor(a!)? running_mean, Tensor(b!)? running_var, Tensor(c!) sums, float momentum, "
-        "float eps, bool relu, int phases=0) -> (Tensor, Tensor, Tensor)",
+        "float eps, bool relu, int phases=0, Tensor? workspace=None) -> (Tensor, Tensor, Tensor)",
         &bn_forward);
   m.def("bn_backward(Tensor x, Tensor dy, Tensor gamma, Tensor beta, Tensor mean, Tensor invstd, Tensor? keys, Tensor(a!) S1, "
         "Tensor(b!) S2, int K, Tensor(c!) sums, bool relu, bool need_dx, int phases=0) -> (Tensor, Tensor, Tensor)",

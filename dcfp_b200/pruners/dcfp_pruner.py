@@ -9,6 +9,8 @@ the arithmetic runs in the sm_100a kernels behind torch.ops.dcfp (no CPU fallbac
   * `get_thresh`          CPU torch.sort per group -> exact radix select (`dcfp_thresh_mask`);
   * `gen_channel_mask`    per-layer gt / sum / sort -> one CTA per layer in the same call.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -33,11 +35,20 @@ class dcfp_pruning():
         offs = [0]
         for s in sizes:
             offs.append(offs[-1] + s)
-        self._flat = torch.empty(offs[-1], dtype=torch.float32, device=device)
+        flat = torch.zeros(offs[-1], dtype=torch.float32, device=device)
+        fresh = []  # layers without a score yet (int 0): their first update treats eic as 0, like the reference (:13,:19-20)
+        for (name, _), a, b in zip(layers, offs[:-1], offs[1:]):
+            old = self.state_dict['eic'].get(name, 0)
+            if torch.is_tensor(old):  # re-bind (the set of scored layers changed): keep what was accumulated
+                flat[a:b].copy_(old.to(device).reshape(-1))
+            else:
+                fresh.append(name)
+        self._flat = flat
         self._offsets = torch.tensor(offs, dtype=torch.int32).to(device)
         self._names = [n for n, _ in layers]
         for (name, _), a, b in zip(layers, offs[:-1], offs[1:]):
             self.state_dict['eic'][name] = self._flat[a:b]  # per-layer views of the one score vector
+        return len(fresh) == len(layers)
 
     def step(self, model):
         """eic = eic*r + (flag*|grad| + !flag*eic)*(1-r), flag = grad*gamma > 0   (reference :15-20)."""
@@ -50,16 +61,20 @@ class dcfp_pruning():
             if not m.weight.is_cuda:
                 raise RuntimeError("dcfp_pruning.step: %s lives on %s; the EIC update runs on the GPU only" % (name, m.weight.device))
         ops.require_gpu()
-        first = self._flat is None
-        if first or self._names != [n for n, _ in layers]:
-            self._bind(layers)
-            first = True
+        first = False
+        if self._flat is None or self._names != [n for n, _ in layers]:
+            # first = "every layer starts from the int 0 state": the kernel then skips reading eic.  A re-bind that carries
+            # accumulated scores over takes the general path: zero-initialised entries give the same bits (0*r + g*(1-r)).
+            first = self._bind(layers)
         with torch.no_grad():
             ops.eic_update([m.weight.grad.detach().contiguous() for _, m in layers],
                            [m.weight.detach().contiguous() for _, m in layers], self._offsets, self._flat, self.r, first)
 
     def get_eic(self):
-        return self.state_dict
+        """{'eic': {name: Tensor[C] | int 0}}.  The per-layer tensors of `self.state_dict` are views of ONE flat device
+        vector that `step` updates in place; the reference rebinds fresh tensors every step (:20), so what a caller got
+        earlier keeps its values there.  Same behaviour here: the returned tensors are copies."""
+        return {'eic': {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.state_dict['eic'].items()}}
 
     def export_eic(self, path):
         out = {'eic': {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.state_dict['eic'].items()}}
@@ -73,6 +88,7 @@ class DCFPPruner(ChannelPruner):
         self.global_percent = global_percent
         self.eic = torch.load(score_file, map_location='cpu')['eic']
         self._thresh = None
+        self._selected = None  # (key, result) of the last K2 call: get_thresh() + gen_channel_mask() share one launch
 
     def get_bn_group(self, bn_layer):
         return 0 if bn_layer.startswith('backbone') else 1
@@ -83,8 +99,13 @@ class DCFPPruner(ChannelPruner):
     def _select(self):
         """One K2 call: thresholds over the BNs outside `except_layers` (:43-66) and masks for every
         link whose CONV is outside `except_layers` (:68-92).  Returns (thresh[2], {bn: mask})."""
+        key = (self.global_percent, self.layer_keep, id(self.eic), tuple(self.norm_conv_links.items()), tuple(sorted(self.except_layers)))
+        if self._selected is not None and self._selected[0] == key:
+            return self._selected[1]
         ops.require_gpu()
         device = ops.device()
+        if os.environ.get("DCFP_TRACE_BACKEND"):
+            print("dcfp backend: cuda (%s), torch.ops.dcfp abi v%d" % (torch.cuda.get_device_name(device), int(ops.load().abi_version())), flush=True)
         layers, scores, groups, min_keep = [], [], [], []
         bn_size = [0, 0]
         for bn_layer, conv_layer in self.norm_conv_links.items():
@@ -121,7 +142,9 @@ class DCFPPruner(ChannelPruner):
         for (bn_layer, needs_mask), a, b in zip(layers, offs[:-1], offs[1:]):
             if needs_mask:
                 out[bn_layer] = mask[a:b].clone()
-        return [thresh[g] if bn_size[g] > 0 else 0 for g in (0, 1)], out
+        res = ([thresh[g] if bn_size[g] > 0 else 0 for g in (0, 1)], out)
+        self._selected = (key, res)
+        return res
 
     def get_thresh(self):
         thresh, _ = self._select()

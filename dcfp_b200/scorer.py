@@ -56,16 +56,9 @@ class _FusedBN(torch.autograd.Function):
                 if sc.track_counters:
                     module.num_batches_tracked.add_(1)
         sums_f, sums_b = sc._bn_scratch(layer)
-        nb = x.numel() * x.element_size()
-        if sc.timing:  # the two passes timed apart
-            t = sc._t_begin()
-            _, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, phases=1)
-            sc._t_end(t, "bn_fwd_stats", nb)
-            t = sc._t_begin()
-            y, _, _ = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, phases=2)
-            sc._t_end(t, "bn_fwd_apply", 2 * nb)
-        else:
-            y, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu)
+        t = sc._t_begin()
+        y, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, workspace=sc._bn_workspace)
+        sc._t_end(t, "bn_fwd", 2 * x.numel() * x.element_size())
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.layer, ctx.relu, ctx.sums_b = layer, relu, sums_b
         return y
@@ -191,12 +184,14 @@ class ClassStatsScorer:
         self.phase_events = []  # (kind, start, end, algorithmic bytes) of the fused BN passes when timing
         # fused BN: one scratch per layer and direction (striped fp64 partial sums + coefficient vectors, csrc/bn_common.cuh),
         # all of them in one flat buffer zeroed once per step
-        self._bn_ws = None
+        self._bn_ws = self._bn_workspace = None
         if self.fused:
             self._bn_ws_off = [0]
             for c in sizes:
                 self._bn_ws_off.append(self._bn_ws_off[-1] + ops.bn_scratch_elems(c))
             self._bn_ws = torch.zeros(2 * self._bn_ws_off[-1], dtype=torch.float64, device=self.device)
+            # per-CTA partial sums of the one-launch forward: unzeroed, shared by all layers (stream-ordered)
+            self._bn_workspace = ops.bn_workspace(max(sizes), self.device)
         self._fused_layers = {n: _FusedLayer(self, n, m, self._views[n][0], self._views[n][1], i)
                               for i, (n, m) in enumerate(self.layers)} if self.fused else {}
         self._fused_calls = {}
@@ -497,7 +492,8 @@ class ClassStatsScorer:
 
     def phase_times(self):
         """{kind: (ms, algorithmic bytes, calls)} of the fused BN passes (timing=True) -- call after a synchronize.
-        kinds: bn_fwd_stats (F1), bn_fwd_apply (F2), bn_bwd_reduce (B1: the class-keyed reduction), bn_bwd_dx (B2)."""
+        kinds: bn_fwd (statistics + normalise, one cooperative launch), bn_bwd_reduce (B1: the class-keyed reduction),
+        bn_bwd_dx (B2)."""
         out = {}
         for kind, e0, e1, nb in self.phase_events:
             ms, b, n = out.get(kind, (0.0, 0, 0))

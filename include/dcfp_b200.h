@@ -214,9 +214,14 @@ typedef struct dcfp_bn_desc {
                             beta [+ S1/S2]); 2: only the element-wise pass (needs the scratch a phase-1 call left) --
                             lets a caller time the two apart */
   int32_t reserved;      /* must be 0 */
+  void* workspace;       /* forward: dcfp_bn_workspace_bytes(C) bytes of device scratch, NOT zeroed, reusable by every
+                            call on the same stream (per-CTA partial sums of the one-launch forward); NULL selects the
+                            two-launch forward */
+  int64_t workspace_bytes;
 } dcfp_bn_desc;
 int dcfp_bn_supported(int N, int C, int h, int w, int dtype);
 size_t dcfp_bn_scratch_bytes(int C);
+size_t dcfp_bn_workspace_bytes(int C);
 int dcfp_bn_forward(const dcfp_bn_desc* desc_host, void* stream);
 int dcfp_bn_backward(const dcfp_bn_desc* desc_host, void* stream);
 

@@ -1,9 +1,10 @@
 """Import the UNMODIFIED reference (wzx99/DCFP) in the build container.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  `/root/reference` does not exist
-on the GPU box, so everything here is used (a) by ``tests/golden/make_golden.py`` to
-generate committed fixtures and (b) by ``-m "not gpu"`` tests that are skipped when
-the reference tree is absent.
+on the GPU box; ``scripts/vendor_reference.py`` leaves a byte-identical copy of its Python
+sources in the git-ignored ``baseline/_ref/``, which does travel.  Used (a) by
+``tests/golden/make_golden.py`` to generate committed fixtures, (b) by tests marked ``ref``
+(skipped when no reference tree is found) and (c) by ``bench.py --impl reference``.
 
 Three external shims are needed to run the reference under torch 2.11 / py3.12
 (SURVEY.md section 8c); none of them carries arithmetic:
@@ -22,7 +23,17 @@ import sys
 import types
 import contextlib
 
-REF_ROOT = os.environ.get("DCFP_REF", "/root/reference")
+def _find_reference():
+    """$DCFP_REF, else the read-only tree of the build container, else the byte-identical copy that
+    scripts/vendor_reference.py leaves in the git-ignored baseline/_ref/ (the only one present on the GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("DCFP_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "pruners", "dcfp_pruner.py")):
+            return cand
+    return os.environ.get("DCFP_REF", "/root/reference")
+
+
+REF_ROOT = _find_reference()
 
 
 def available() -> bool:

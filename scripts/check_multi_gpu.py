@@ -64,6 +64,15 @@ if rank == 0:
     same = (m1 == m2).float().mean().item()
     print("masks @0.5: %.4f %% of channels agree; thresholds %s vs %s" % (100 * same, t1.tolist(), t2.tolist()))
     assert same > 0.995
+    # threshold margins: how far the nearest score is from each threshold, and -- if a keep bit differs
+    # between the N-rank pass and the single-GPU replay -- how close to its threshold that channel sits
+    from dcfp_b200.pruners.margin import compare_masks, format_margins
+    off_h, grp_h = offs.cpu().tolist(), groups.cpu().tolist()
+    cmp = compare_masks(eic_dist, eic_one, off_h, grp_h, 0.5)
+    print("margin min|score - thresh|/thresh  N ranks: %s | replay: %s" % (format_margins(cmp["margins_a"]), format_margins(cmp["margins_b"])))
+    print("keep bits that differ: %d of %d; they lie within %.3g of their threshold (relative); score discrepancy near the "
+          "thresholds: %.3g" % (cmp["flipped"], cmp["n"], cmp["flip_band"], cmp["disc_near"]))
+    assert cmp["flip_band"] <= max(4 * cmp["disc_near"], 1e-6), "a mask bit flipped outside the band the score discrepancy explains"
     # the all-reduced class statistics: sum over ALL micro-batches of S1 == totals of the replay
     tot1 = sc.totals[0].cpu()
     name = sc.names[7]

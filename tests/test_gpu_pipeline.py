@@ -48,6 +48,21 @@ def test_score_then_prune_identical_to_oracle_backend(native, tmp_path, arch, cl
     sa, sb = sub_gpu.state_dict(), sub_cpu.state_dict()
     assert list(sa.keys()) == list(sb.keys())
     assert all(torch.equal(sa[k].cpu(), sb[k].cpu()) for k in sa)
+    # a second scoring stack on the same images -- torch/cuDNN BatchNorm + ReLU with the hook-fed K1 instead of the fused
+    # BN kernels: scores agree to a tolerance only, so the masks are compared WITH the threshold margin:
+    # a keep bit may differ only for a channel that sits within the score discrepancy of its threshold
+    from dcfp_b200.pruners.margin import compare_masks, format_margins
+    out_b = score_calibration_set(copy.deepcopy(base).to("cuda").to(memory_format=torch.channels_last), x, y, classes,
+                                  micro_batch=2, r=0.999, seed=0, fused=False)
+    names = list(out["eic"].keys())
+    sizes = [out["eic"][n].numel() for n in names]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    grp = [0 if n.startswith("backbone") else 1 for n in names]
+    cmp = compare_masks(flat, np.concatenate([out_b["eic"][n].numpy() for n in names]), offs, grp, gp)
+    print("fused vs unfused stack @ global_percent %.2f: %s | %s; %d / %d keep bits differ, all within %.3g of their "
+          "threshold; score discrepancy near the thresholds %.3g" % (gp, format_margins(cmp["margins_a"]),
+          format_margins(cmp["margins_b"]), cmp["flipped"], cmp["n"], cmp["flip_band"], cmp["disc_near"]))
+    assert cmp["flipped"] <= 0.10 * cmp["n"] and cmp["flip_band"] <= max(4 * cmp["disc_near"], 1e-6)
     kept = sum(c["out_channels"] for c in cfg_gpu.values())
     raw = sum(c["raw_out_channels"] for c in cfg_gpu.values())
     assert kept < raw
