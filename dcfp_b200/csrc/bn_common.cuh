@@ -3,15 +3,16 @@
 //
 // Same-address fp64 atomics serialise in the L2 slice at ~38 cycles each (measured: a per-layer K1 launch whose 1 184
 // warps each added their rows to the same 2*C addresses spent 20-60 us in that tail).  So per-channel totals go to one of
-// kBnStripes copies (stripe = blockIdx % kBnStripes), after a CTA-level combine, and the LAST CTA of the reduction kernel
-// (ticket counter) sums the stripes once, does the fp64 arithmetic once per channel and leaves five fp32 coefficient
-// vectors for the element-wise pass -- whose 500+ blocks then start with eight coalesced loads instead of fp64 math.
+// kBnStripes copies (stripe = blockIdx % kBnStripes), after a CTA-level combine.  The element-wise kernel that follows on
+// the stream sums the stripes of ITS channels in its prologue (bn_coef_forward / bn_coef_backward: a few dozen L2 loads
+// and ~10 fp64 operations per channel, in parallel in every block) -- a "last CTA finalises" step inside the reduction
+// kernel was measured at 4-5 us of serial tail per launch (fence + ticket + one CTA doing all channels).
 #pragma once
 #include "common.cuh"
 
 namespace dcfp {
 
-constexpr int kBnStripes = 8;
+constexpr int kBnStripes = 4;
 
 constexpr int kBnMaxCtas = 512;  // grid-barrier flags of the cooperative kernels (one per CTA; grids are <= #SMs)
 
@@ -69,7 +70,87 @@ __device__ __forceinline__ void bn_sum_stripes(const double* stripes, int C, int
   }
 }
 
-// forward: stripes hold (sum x, sum x^2).  coef[0] = scale = gamma * invstd, coef[1] = shift = fma(-mean, scale, beta):
+// stripe sums of 4 consecutive channels (c0 % 4 == 0): 128-bit read-only loads through L1 -- the stripes were written by the
+// PREVIOUS kernel on the stream, and the blocks of an SM all read the same few KB
+__device__ __forceinline__ void bn_sum_stripes4(const double* stripes, int C, int c0, double* s0, double* s1) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s0[j] = s1[j] = 0.0;
+#pragma unroll
+  for (int s = 0; s < kBnStripes; ++s) {
+    const double2* p0 = reinterpret_cast<const double2*>(stripes + static_cast<size_t>(s) * 2 * C + c0);
+    const double2* p1 = reinterpret_cast<const double2*>(stripes + static_cast<size_t>(s) * 2 * C + C + c0);
+    const double2 a = __ldg(p0), b = __ldg(p0 + 1), c = __ldg(p1), d = __ldg(p1 + 1);
+    s0[0] += a.x, s0[1] += a.y, s0[2] += b.x, s0[3] += b.y;
+    s1[0] += c.x, s1[1] += c.y, s1[2] += d.x, s1[3] += d.y;
+  }
+}
+
+// Per-channel coefficients from the stripes, for the thread that owns channels c0 .. c0 + 3 (element-wise kernels' prologue).
+// forward: stripes hold (sum x, sum x^2)
+__device__ __forceinline__ void bn_coef_forward4(const BnFinal& F, int c0, float* mean_f, float* invstd_f, float* scale, float* shift,
+                                                 double* mean, double* var) {
+  double s[4], q[4];
+  bn_sum_stripes4(bn_stripes(F.scratch), F.C, c0, s, q);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(F.gamma + c0)), b = __ldg(reinterpret_cast<const float4*>(F.beta + c0));
+  const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mean[j] = s[j] * F.inv_m;
+    var[j] = fmax(q[j] * F.inv_m - mean[j] * mean[j], 0.0);
+    mean_f[j] = static_cast<float>(mean[j]);
+    invstd_f[j] = static_cast<float>(rsqrt(var[j] + static_cast<double>(F.eps)));
+    // the SAME two fp32 expressions are re-evaluated by the backward kernels from the saved mean / invstd: bit-exact ReLU gate
+    scale[j] = __fmul_rn(gg[j], invstd_f[j]);
+    shift[j] = __fmaf_rn(-mean_f[j], scale[j], bb[j]);
+  }
+}
+// backward: stripes hold (sum dz, sum dz * xhat);  dx = a * dz + b * x + d,  gate z = fma(x, zs, zt)
+__device__ __forceinline__ void bn_coef_backward4(const BnFinal& F, int c0, float* a_f, float* b_f, float* d_f, float* zs, float* zt,
+                                                  double* dgamma, double* dbeta) {
+  bn_sum_stripes4(bn_stripes(F.scratch), F.C, c0, dbeta, dgamma);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(F.gamma + c0)), b = __ldg(reinterpret_cast<const float4*>(F.beta + c0));
+  const float4 m = __ldg(reinterpret_cast<const float4*>(F.mean + c0)), is = __ldg(reinterpret_cast<const float4*>(F.invstd + c0));
+  const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w}, mm[4] = {m.x, m.y, m.z, m.w}, ii[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double a = static_cast<double>(gg[j]) * ii[j];
+    const double mg = dgamma[j] * F.inv_m, mb = dbeta[j] * F.inv_m;
+    a_f[j] = static_cast<float>(a);
+    b_f[j] = static_cast<float>(-a * ii[j] * mg);
+    d_f[j] = static_cast<float>(a * (static_cast<double>(mm[j]) * ii[j] * mg - mb));
+    zs[j] = __fmul_rn(gg[j], ii[j]);
+    zt[j] = __fmaf_rn(-mm[j], zs[j], bb[j]);
+  }
+}
+
+// single-channel forms
+__device__ __forceinline__ void bn_coef_forward(const BnFinal& F, int c, float& mean_f, float& invstd_f, float& scale, float& shift,
+                                                double& mean, double& var) {
+  double s, q;
+  bn_sum_stripes(bn_stripes(F.scratch), F.C, c, s, q);
+  mean = s * F.inv_m;
+  var = fmax(q * F.inv_m - mean * mean, 0.0);
+  mean_f = static_cast<float>(mean);
+  invstd_f = static_cast<float>(rsqrt(var + static_cast<double>(F.eps)));
+  // the SAME two fp32 expressions are re-evaluated by the backward kernels from the saved mean / invstd: bit-exact ReLU gate
+  scale = __fmul_rn(F.gamma[c], invstd_f);
+  shift = __fmaf_rn(-mean_f, scale, F.beta[c]);
+}
+// backward: stripes hold (sum dz, sum dz * xhat);  dx = a * dz + b * x + d,  gate z = fma(x, zs, zt)
+__device__ __forceinline__ void bn_coef_backward(const BnFinal& F, int c, float& a_f, float& b_f, float& d_f, float& zs, float& zt,
+                                                 double& dgamma, double& dbeta) {
+  bn_sum_stripes(bn_stripes(F.scratch), F.C, c, dbeta, dgamma);
+  const float mean_f = F.mean[c], invstd_f = F.invstd[c], g = F.gamma[c];
+  const double a = static_cast<double>(g) * invstd_f;
+  const double mg = dgamma * F.inv_m, mb = dbeta * F.inv_m;
+  a_f = static_cast<float>(a);
+  b_f = static_cast<float>(-a * invstd_f * mg);
+  d_f = static_cast<float>(a * (static_cast<double>(mean_f) * invstd_f * mg - mb));
+  zs = __fmul_rn(g, invstd_f);
+  zt = __fmaf_rn(-mean_f, zs, F.beta[c]);
+}
+
+// (cooperative forward / tests) forward: stripes hold (sum x, sum x^2).  coef[0] = scale = gamma * invstd, coef[1] = shift = fma(-mean, scale, beta):
 // the backward re-evaluates these two fp32 expressions from the saved mean / invstd, so the ReLU gate is bit-exact.
 __device__ __forceinline__ void bn_finalize_forward(const BnFinal& F) {
   float* coef = bn_coef(F.scratch, F.C);

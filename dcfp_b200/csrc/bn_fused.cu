@@ -163,12 +163,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const BnArgs A, co
       atomicAdd(stripe + A.C + c0 + j, static_cast<double>(s2[j]));
     }
   }
-  if (bn_last_cta(bn_counter(F.scratch, F.C))) bn_finalize_forward(F);
 }
 
-// F2: y = [relu](fma(x, scale, shift)) with the coefficient pair the reduction pass left.
+// F2: y = [relu](fma(x, scale, shift)); scale / shift from the stripes the statistics pass left (every thread for its own
+// channels); block 0 publishes mean / invstd and updates the running statistics.
 template <typename T, bool RELU>
-__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A) {
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A, const BnFinal F) {
   constexpr int kCh = Vec<T>::kCh;
   const int lpr = A.C / kCh;
   const BnThread th(lpr);
@@ -180,11 +180,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A) {
     const int cg = cb + th.tc;
     if (!th.active || cg >= lpr) continue;
     const int c0 = cg * kCh;
-    float scale[kCh], shift[kCh];
+    float scale[kCh], shift[kCh], mean_f[kCh], invstd_f[kCh];
+    double mean[kCh], var[kCh];
 #pragma unroll
-    for (int j = 0; j < kCh; ++j) {
-      scale[j] = A.coef[c0 + j];
-      shift[j] = A.coef[A.C + c0 + j];
+    for (int q = 0; q < kCh; q += 4) bn_coef_forward4(F, c0 + q, mean_f + q, invstd_f + q, scale + q, shift + q, mean + q, var + q);
+    if (blockIdx.x == 0 && th.tr == 0) {
+#pragma unroll
+      for (int j = 0; j < kCh; ++j) {
+        F.mean[c0 + j] = mean_f[j];
+        F.invstd[c0 + j] = invstd_f[j];
+        if (F.running_mean != nullptr) {
+          F.running_mean[c0 + j] = static_cast<float>((1.0 - F.momentum) * F.running_mean[c0 + j] + F.momentum * mean[j]);
+          F.running_var[c0 + j] = static_cast<float>((1.0 - F.momentum) * F.running_var[c0 + j] + F.momentum * var[j] * F.unbias);
+        }
+      }
     }
     for (long long r = r1 - 1 - th.tr; r >= r0; r -= static_cast<long long>(th.rpp) * kBnUnroll) {
       float v[kBnUnroll][kCh];
@@ -209,9 +218,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A) {
   }
 }
 
-// B2: dx = a * dz + b * x + d per channel, with dz = (fma(x, zscale, zshift) > 0) ? dy : 0 when RELU.
+// B2: dx = a * dz + b * x + d per channel, with dz = (fma(x, zscale, zshift) > 0) ? dy : 0 when RELU; the coefficients from the
+// stripes B1 left (sum dz, sum dz * xhat); block 0 publishes dgamma / dbeta.  A.y == NULL: only those two are wanted.
 template <typename T, bool RELU>
-__global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A) {
+__global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A, const BnFinal F) {
   constexpr int kCh = Vec<T>::kCh;
   const int lpr = A.C / kCh;
   const BnThread th(lpr);
@@ -225,14 +235,17 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A) {
     if (!th.active || cg >= lpr) continue;
     const int c0 = cg * kCh;
     float zs[kCh], zt[kCh], ca[kCh], cb_[kCh], cd[kCh];
+    double dgamma[kCh], dbeta[kCh];
 #pragma unroll
-    for (int j = 0; j < kCh; ++j) {
-      ca[j] = A.coef[c0 + j];
-      cb_[j] = A.coef[A.C + c0 + j];
-      cd[j] = A.coef[2 * A.C + c0 + j];
-      zs[j] = A.coef[3 * A.C + c0 + j];
-      zt[j] = A.coef[4 * A.C + c0 + j];
+    for (int q = 0; q < kCh; q += 4) bn_coef_backward4(F, c0 + q, ca + q, cb_ + q, cd + q, zs + q, zt + q, dgamma + q, dbeta + q);
+    if (blockIdx.x == 0 && th.tr == 0) {
+#pragma unroll
+      for (int j = 0; j < kCh; ++j) {
+        F.dgamma[c0 + j] = static_cast<float>(dgamma[j]);
+        F.dbeta[c0 + j] = static_cast<float>(dbeta[j]);
+      }
     }
+    if (dx == nullptr) continue;
     for (long long r = r1 - 1 - th.tr; r >= r0; r -= static_cast<long long>(th.rpp) * kBnUnroll) {
       float vx[kBnUnroll][kCh], vg[kBnUnroll][kCh];
 #pragma unroll
@@ -263,7 +276,10 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A) {
 int validate_bn(const dcfp_bn_desc* d, bool backward) {
   DCFP_REQUIRE(d != nullptr, DCFP_EINVAL, "bn: null descriptor");
   DCFP_REQUIRE(d->x && d->gamma && d->beta && d->mean && d->invstd && d->scratch, DCFP_EINVAL, "bn: null pointer (x/gamma/beta/mean/invstd/scratch)");
-  DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->scratch) % 8 == 0, DCFP_EINVAL, "bn: scratch must be 8-byte aligned");
+  DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->scratch) % 16 == 0, DCFP_EINVAL, "bn: scratch must be 16-byte aligned");
+  DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->gamma) % 16 == 0 && reinterpret_cast<uintptr_t>(d->beta) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(d->mean) % 16 == 0 && reinterpret_cast<uintptr_t>(d->invstd) % 16 == 0,
+               DCFP_EUNSUPPORTED, "bn: gamma / beta / mean / invstd must be 16-byte aligned");
   DCFP_REQUIRE(d->N > 0 && d->C > 0 && d->h > 0 && d->w > 0, DCFP_EINVAL, "bn: bad extent N=%d C=%d h=%d w=%d", d->N, d->C, d->h, d->w);
   DCFP_REQUIRE(d->dtype == DCFP_F32 || d->dtype == DCFP_BF16, DCFP_EINVAL, "bn: unknown dtype %d", d->dtype);
   DCFP_REQUIRE(d->phases >= 0 && d->phases <= 2 && d->reserved == 0, DCFP_EINVAL, "bn: bad phases (%d) / reserved field", d->phases);
@@ -347,9 +363,9 @@ int forward_t(const dcfp_bn_desc* d, cudaStream_t stream) {
     if (rc || d->phases == 1) return rc;
   }
   A.y = d->y;
-  const BnArgs P = plan_rows<T>(A, 4, &grid);
-  if (d->relu) bn_apply_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P);
-  else bn_apply_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P);
+  const BnArgs P = plan_rows<T>(A, 3, &grid);  // 73 registers / thread: 3 blocks of 256 per SM
+  if (d->relu) bn_apply_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
+  else bn_apply_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
   return finish_launch("bn_apply");
 }
 
@@ -360,8 +376,9 @@ int backward_dx_t(const dcfp_bn_desc* d, cudaStream_t stream) {
   A.y = d->dx;
   dim3 grid;
   const BnArgs P = plan_rows<T>(A, 2, &grid);
-  if (d->relu) bn_dx_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P);
-  else bn_dx_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P);
+  if (d->dx == nullptr) grid = dim3(1);  // gradients of gamma / beta only
+  if (d->relu) bn_dx_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
+  else bn_dx_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
   return finish_launch("bn_dx");
 }
 
@@ -420,6 +437,5 @@ extern "C" int dcfp_bn_backward(const dcfp_bn_desc* d, void* stream_) {
     rc = k1_run_bn_backward(L, final_args(d), d->relu != 0, stream);  // B1 (+ finalisation by its last CTA)
     if (rc || d->phases == 1) return rc;
   }
-  if (d->dx == nullptr) return 0;  // dgamma / dbeta were written by B1's last CTA
   return d->dtype == DCFP_F32 ? backward_dx_t<float>(d, stream) : backward_dx_t<__nv_bfloat16>(d, stream);
 }

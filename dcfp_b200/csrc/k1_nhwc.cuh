@@ -61,6 +61,8 @@ struct NhwcParams {
   int32_t K;
   int32_t stages;   // boxes in flight per warp
   int32_t keep_l2;  // 0: read-once stream (evict-first); 1: a second pass re-reads these maps (normal L2 priority)
+  int32_t debug_skip_rows;  // DCFP_K1_DEBUG_SKIP_ROWS=1: drop the class-row atomics (timing experiments only; results wrong)
+  int32_t contig;   // 1: every phase of a CTA walks one contiguous run of its chunk's pixel groups (per-layer launches)
 };
 // BN-backward fusion (FUSED != 0; one layer per launch): the value functor becomes v = dz * xhat with the ReLU gate
 // recomputed from the forward's own z = fma(x, zscale, zshift) (FUSED == 2), and the launch also yields the two
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       b.z += __shfl_xor_sync(0xffffffffu, b.z, 16);
       b.w += __shfl_xor_sync(0xffffffffu, b.w, 16);
     }
-    if (lane_on && !(fold2 && lane >= 16)) {
+    if (lane_on && !(fold2 && lane >= 16) && !P.debug_skip_rows) {
       double* d1 = out1 + cls * ld;
       double* d2 = out2 + cls * ld;
       if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));
@@ -378,7 +380,15 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     const int p_begin = chunk * L.px_per_chunk;
     const int p_end = min(p_begin + L.px_per_chunk, L.n_px);
     const int n_groups = (p_end - p_begin + G - 1) / G;
-    const int n_my = col0 < L.C ? (n_groups - phase + phases - 1) / phases : 0;  // a warp whose slab is empty idles
+    // Which pixel groups of the chunk this warp takes.  Grouped launches interleave the phases (group = phase + it * phases:
+    // the warps of a CTA read adjacent boxes at the same time).  Per-layer launches (P.contig) give every phase ONE
+    // contiguous run of groups instead: a warp then sees the few classes of a short stretch of one image row, not every
+    // class of the chunk -- with fragmented label maps or K = 150 / 171 that is the difference between no slot-cache
+    // evictions and one per few pixels (each eviction = 256 fp64 atomics).
+    const int per_phase = (n_groups + phases - 1) / phases;
+    const int g_first = P.contig ? min(phase * per_phase, n_groups) : phase;
+    const int g_stride = P.contig ? 1 : phases;
+    const int n_my = col0 >= L.C ? 0 : (P.contig ? min(per_phase, n_groups - g_first) : (n_groups - phase + phases - 1) / phases);  // a warp whose slab is empty idles
 
     int issue_it = 0, issue_stage = 0;
     auto issue = [&]() {  // one elected lane arms the barrier and launches the tile copies of the warp's next group
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
         if (lane == 0) {
           const uint32_t bar = my_bars + issue_stage * 8;
           const uint32_t dst = my_bufs + issue_stage * kStageBytes;
-          const int p = p_begin + (phase + issue_it * phases) * G;
+          const int p = p_begin + (g_first + issue_it * g_stride) * G;
           mbar_expect_tx(bar, kStageBytes);
           tma_load_2d(dst, maps, col0, p, bar, policy);  // rows past n_px / columns past C arrive as zeros
           if (BWD) tma_load_2d(dst + kNhwcBoxBytes, maps + 1, col0, p, bar, policy);
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
 #pragma unroll
       for (int q = 0; q < 2 * Q; ++q) dst[q] = dropped;
       if (it < n_my) {
-        const int p = p_begin + (phase + it * phases) * G;
+        const int p = p_begin + (g_first + it * g_stride) * G;
         if (p + G <= p_end) {
 #pragma unroll
           for (int q = 0; q < 2 * Q; ++q)
@@ -549,9 +559,6 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     }
   }
   if (cur_layer >= 0) fold();
-  if (FUSED) {  // the last CTA turns the stripes into dgamma / dbeta and the dx coefficients
-    if (bn_last_cta(bn_counter(F.fin.scratch, F.fin.C))) bn_finalize_backward(F.fin);
-  }
 }
 
 // NHWC: [rows = N*HW][cols = C], box = [G px][128 channels], no swizzle (a pixel row is read with one LDS per lane)
@@ -604,6 +611,16 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPl
   P.n_layers = n;
   P.K = K;
   P.keep_l2 = plan.keep_l2 ? 1 : 0;
+  static const int no_contig = []() {
+    const char* e = getenv("DCFP_K1_NO_CONTIG");
+    return e ? atoi(e) : 0;
+  }();
+  P.contig = (plan.single_wave && !no_contig) ? 1 : 0;
+  static const int skip_rows = []() {
+    const char* e = getenv("DCFP_K1_DEBUG_SKIP_ROWS");
+    return e ? atoi(e) : 0;
+  }();
+  P.debug_skip_rows = skip_rows;
   P.tile_prefix[0] = 0;
   bool affine = false;
   for (int i = 0; i < n; ++i) {

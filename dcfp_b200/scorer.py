@@ -182,6 +182,7 @@ class ClassStatsScorer:
         self.k1_events = []  # (start, end, algorithmic bytes) per K1 launch when timing
         self.k1_bytes = 0
         self.phase_events = []  # (kind, start, end, algorithmic bytes) of the fused BN passes when timing
+        self._phase_acc, self._k1_acc = {}, (0.0, 0, 0)  # totals over graph replays (accumulate_timing)
         # fused BN: one scratch per layer and direction (striped fp64 partial sums + coefficient vectors, csrc/bn_common.cuh),
         # all of them in one flat buffer zeroed once per step
         self._bn_ws = self._bn_workspace = None
@@ -190,8 +191,13 @@ class ClassStatsScorer:
             for c in sizes:
                 self._bn_ws_off.append(self._bn_ws_off[-1] + ops.bn_scratch_elems(c))
             self._bn_ws = torch.zeros(2 * self._bn_ws_off[-1], dtype=torch.float64, device=self.device)
-            # per-CTA partial sums of the one-launch forward: unzeroed, shared by all layers (stream-ordered)
-            self._bn_workspace = ops.bn_workspace(max(sizes), self.device)
+            # DCFP_BN_COOP=1: the one-launch cooperative forward (bit-reproducible statistics, no atomics; csrc/bn_coop.cuh)
+            # instead of the statistics + normalise kernel pair, which measures faster on every c2 layer shape
+            # (13.5 vs 23 us on a 17 MB layer, 36 vs 40 us on a 67 MB one).  Its per-CTA partial sums live in this
+            # unzeroed workspace shared by all layers (stream-ordered).
+            import os
+            if os.environ.get("DCFP_BN_COOP", "0") == "1":
+                self._bn_workspace = ops.bn_workspace(max(sizes), self.device)
         self._fused_layers = {n: _FusedLayer(self, n, m, self._views[n][0], self._views[n][1], i)
                               for i, (n, m) in enumerate(self.layers)} if self.fused else {}
         self._fused_calls = {}
@@ -275,19 +281,37 @@ class ClassStatsScorer:
         a, b, half = self._bn_ws_off[layer.index], self._bn_ws_off[layer.index + 1], self._bn_ws_off[-1]
         return self._bn_ws[a:b], self._bn_ws[half + a:half + b]
 
-    def _t_begin(self):
-        if not self.timing:
-            return None
-        e = torch.cuda.Event(enable_timing=True)
+    @staticmethod
+    def _event():
+        """A timing event; inside a CUDA-graph capture an EXTERNAL one (an event-record node: its timestamp is rewritten by
+        every replay, so kernels can be timed in situ without the host's launch rate in the picture)."""
+        e = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
         e.record()
         return e
+
+    def _t_begin(self):
+        return self._event() if self.timing else None
 
     def _t_end(self, e0, kind, nbytes):
         if e0 is None:
             return
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
-        self.phase_events.append((kind, e0, e1, nbytes))
+        self.phase_events.append((kind, e0, self._event(), nbytes))
+
+    def accumulate_timing(self):
+        """After a synchronised graph replay: add the elapsed times of the captured (external) events to the running totals
+        (`phase_times()` / `k1_time_ms()` then report the totals over all replays)."""
+        for kind, e0, e1, nb in self.phase_events:
+            ms, b, n = self._phase_acc.get(kind, (0.0, 0, 0))
+            self._phase_acc[kind] = (ms + e0.elapsed_time(e1), b + nb, n + 1)
+        ms, b, n = self._k1_acc
+        self._k1_acc = (ms + sum(e0.elapsed_time(e1) for e0, e1, _ in self.k1_events), b + sum(x for _, _, x in self.k1_events),
+                        n + len(self.k1_events))
+
+    def reset_timing(self, drop_events=True):
+        self._phase_acc, self._k1_acc = {}, (0.0, 0, 0)
+        if drop_events:
+            self.k1_events.clear()
+            self.phase_events.clear()
 
     def set_labels(self, labels):
         """labels of the micro-batch about to run: [N, H0, W0] uint8 / int32 / int64 on the device."""
@@ -316,9 +340,7 @@ class ClassStatsScorer:
         """ONE K1 launch over `items` = [(x, dy|None, scale|None, shift|None, keys, S1, S2)], optionally timed."""
         nbytes = sum(x.numel() * x.element_size() * (2 if dy is not None else 1) + k.numel() for x, dy, _, _, k, _, _ in items)
         if self.timing:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0 = self._event()
         bwd = items[0][1] is not None
         affine = items[0][2] is not None
         # K + 1 classes for the kernel: label_keys maps every label outside [0, K) to the key K, which is row K here
@@ -327,8 +349,7 @@ class ClassStatsScorer:
                                 scales=[i[2] for i in items] if affine else None, shifts=[i[3] for i in items] if affine else None,
                                 affine_mode=ops.AFFINE_INVSTD_MEAN if bwd else ops.AFFINE_SCALE_SHIFT)
         if self.timing:
-            e1.record()
-            self.k1_events.append((e0, e1, nbytes))
+            self.k1_events.append((e0, self._event(), nbytes))
         self.k1_bytes += nbytes
 
     def _flush_fwd(self):
@@ -487,6 +508,8 @@ class ClassStatsScorer:
 
     def k1_time_ms(self):
         """(sum of K1 launch durations in ms, algorithmic bytes, launches) -- call after a synchronize."""
+        if self._k1_acc[2]:
+            return self._k1_acc
         ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.k1_events)
         return ms, sum(b for _, _, b in self.k1_events), len(self.k1_events)
 
@@ -494,6 +517,8 @@ class ClassStatsScorer:
         """{kind: (ms, algorithmic bytes, calls)} of the fused BN passes (timing=True) -- call after a synchronize.
         kinds: bn_fwd (statistics + normalise, one cooperative launch), bn_bwd_reduce (B1: the class-keyed reduction),
         bn_bwd_dx (B2)."""
+        if self._phase_acc:
+            return dict(self._phase_acc)
         out = {}
         for kind, e0, e1, nb in self.phase_events:
             ms, b, n = out.get(kind, (0.0, 0, 0))
@@ -512,28 +537,49 @@ class CalibrationRun:
     all-reduce before the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
 
     def __init__(self, model, num_classes, r=0.999, mode="bwd", restore_bn_stats=True, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, process_group=None, seed=None, scores_only=False, fused=True):
+                 timing=False, process_group=None, seed=None, scores_only=False, fused=True, graph=True):
         ops.require_gpu()
         self.model = model
         self.seed = seed
+        self.scores_only = bool(scores_only)
+        self.restore_bn_stats = bool(restore_bn_stats)
+        self._frozen = []
+        self.device = next(model.parameters()).device
+        # restore_bn_stats puts num_batches_tracked back at close(): the fused layers then skip its per-layer increment
+        self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
+                                       keep_totals=keep_totals, timing=timing, fused=fused,
+                                       track_counters=not restore_bn_stats)
+        self._saved = None
+        self.group = process_group
+        self.closed = True
+        # CUDA graph of one step (forward + backward + fold): a c2 step is ~900 launches issued from Python and the autograd
+        # thread; replaying them from a graph takes the host out of the critical path.  Captured on the third step of a
+        # given input shape (the first learns the BN->ReLU pairs and lets cuDNN autotune, the second runs the final kernels
+        # once eagerly); any failure to capture falls back to eager launches of the SAME kernels.
+        self.graph = bool(graph) and mode == "bwd"
+        self._graph = None       # (key, CUDAGraph, static x, static y, dgamma, loss)
+        self._graph_seen = {}    # input signature -> eager steps run
+        self._graph_grads = []   # (parameter, its .grad tensor inside the graph's pool)
+        self.graph_replays = 0
+        self.graph_launches = 0
+        self._open()
+
+    def _open(self):
+        """Puts the model into scoring state: (scores_only) freeze non-BN parameters, attach hooks / fused forwards, snapshot the
+        BN running statistics, train mode."""
+        model = self.model
         # scores_only: the EIC needs d(loss)/d(gamma) of the BN layers only, and K1 computes it from (x, dy) itself.
         # Freezing every non-BN parameter keeps the activation-gradient chain (dgrad) but drops the weight-gradient
         # convolutions (wgrad, ~17 % of a c2 step) that the reference's training loop needs for its optimizer and a
         # calibration pass does not.  Off by default: the default step does the reference's full backward.
-        self._frozen = []
-        if scores_only:
+        if self.scores_only:
             bn_params = {id(p) for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) for p in m.parameters()}
             for p_ in model.parameters():
                 if id(p_) not in bn_params and p_.requires_grad:
                     p_.requires_grad_(False)
                     self._frozen.append(p_)
-        self.device = next(model.parameters()).device
-        # restore_bn_stats puts num_batches_tracked back at close(): the fused layers then skip its per-layer increment
-        self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
-                                       keep_totals=keep_totals, timing=timing, fused=fused,
-                                       track_counters=not restore_bn_stats).attach()
-        self._saved = None
-        if restore_bn_stats:  # train-mode BN updates its running statistics: snapshot them (a few fused launches)
+        self.scorer.attach()
+        if self.restore_bn_stats:  # train-mode BN updates its running statistics: snapshot them (a few fused launches)
             bns = [m for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.running_mean is not None]
             live = [m.running_mean for m in bns] + [m.running_var for m in bns]
             counters = [m.num_batches_tracked for m in bns]
@@ -541,8 +587,56 @@ class CalibrationRun:
                            torch._foreach_add(counters, 0) if counters else [])
         self._was_training = model.training
         model.train()
-        self.group = process_group
+        for p_, g in self._graph_grads:  # a kept graph writes the gradients into these tensors
+            p_.grad = g
         self.closed = False
+
+    def reopen(self):
+        """A closed run whose CUDA graph was kept (close(keep_graph=True)) scores again from a clean state."""
+        sc = self.scorer
+        sc.steps = 0
+        sc.eic.zero_()
+        sc.step_arena.zero_()
+        if sc.total_arena is not None:
+            sc.total_arena.zero_()
+        else:
+            sc.cnt.zero_()
+        sc._pending, sc._pending_fwd, sc._pending_bytes = [], [], 0
+        sc.k1_events.clear()
+        sc.phase_events.clear()
+        self._open()
+
+    def _forward_backward(self, x, y):
+        sc = self.scorer
+        sc.set_labels(y)
+        self.model.zero_grad(set_to_none=True)
+        out = self.model(x, y if y.dtype == torch.long else y.long(), deepsup=True)
+        loss = out["loss"] if isinstance(out, dict) else out
+        if sc.mode == "bwd":
+            loss.backward()
+        return sc.fold_step(), loss.detach()
+
+    def _capture(self, key, x, y):
+        gx, gy = x.clone(memory_format=torch.preserve_format), y.clone()
+        g = torch.cuda.CUDAGraph()
+        if self.scorer.timing:  # only the events recorded inside the capture are re-stamped by the replays
+            self.scorer.reset_timing()
+        launches0 = ops.launch_count()
+        try:
+            with torch.cuda.graph(g):
+                dgamma, loss = self._forward_backward(gx, gy)
+        except Exception as e:  # not capturable (data-dependent control flow, an op that synchronises, ...): eager from now on
+            import warnings
+            warnings.warn("dcfp_b200: the scoring step could not be captured into a CUDA graph (%s: %s); launching eagerly" %
+                          (type(e).__name__, str(e).split("\n")[0][:200]))
+            self.graph = False
+            self.scorer._pending, self.scorer._pending_fwd, self.scorer._pending_bytes = [], [], 0
+            torch.cuda.synchronize()
+            return False
+        self._graph = (key, g, gx, gy, dgamma, loss)
+        self._graph_grads = [(p_, p_.grad) for p_ in self.model.parameters() if p_.grad is not None]
+        self.graph_launches = ops.launch_count() - launches0  # kernels of this library inside one replay
+        return True
 
     def step(self, x, y, mb_index=None):
         """x [N,3,H,W] fp32, y [N,H,W] integer labels, both ON THE DEVICE.  Returns the loss tensor (device).
@@ -551,19 +645,42 @@ class CalibrationRun:
         sc = self.scorer
         if self.seed is not None and mb_index is not None:
             torch.manual_seed(self.seed + int(mb_index))
-        sc.set_labels(y)
-        self.model.zero_grad(set_to_none=True)
-        out = self.model(x, y if y.dtype == torch.long else y.long(), deepsup=True)
-        loss = out["loss"] if isinstance(out, dict) else out
-        if sc.mode == "bwd":
-            loss.backward()
-        dgamma = sc.fold_step()
+        dgamma = None
+        if self.graph:
+            key = (tuple(x.shape), x.dtype, tuple(x.stride()), tuple(y.shape), y.dtype, sc.timing)
+            if self._graph is not None and self._graph[0] == key:
+                _, g, gx, gy, dgamma, loss = self._graph
+                gx.copy_(x, non_blocking=True)
+                gy.copy_(y, non_blocking=True)
+                g.replay()
+                self.graph_replays += 1
+                if sc.timing:  # in-graph (external) events: read them once the replay has finished
+                    torch.cuda.synchronize()
+                    sc.accumulate_timing()
+            else:
+                seen = self._graph_seen.get(key, 0)
+                self._graph_seen[key] = seen + 1
+                if seen >= 2 and self._capture(key, x, y):  # the captured launches have not run yet: replay them once
+                    _, g, gx, gy, dgamma, loss = self._graph
+                    g.replay()
+                    self.graph_replays += 1
+                    if sc.timing:
+                        torch.cuda.synchronize()
+                        sc.accumulate_timing()
+        if dgamma is None:
+            dgamma, loss = self._forward_backward(x, y)
+        else:
+            dgamma, loss = dgamma.clone(), loss.clone()  # the graph's outputs are overwritten by the next replay
         if sc.mode == "bwd":
             average_over_ranks(dgamma, self.group)
             sc.eic_step(dgamma)
-        return loss.detach()
+        return loss
 
-    def close(self):
+    def close(self, keep_graph=False):
+        """Restores the model (hooks off, running statistics, train / eval mode, requires_grad).  keep_graph: the captured
+        step and its memory pool survive for `reopen()` (score_calibration_set's run cache)."""
+        if not keep_graph:
+            self._graph, self._graph_grads = None, []  # releases the graph's private memory pool
         if self.closed:
             return
         self.closed = True
@@ -583,9 +700,38 @@ class CalibrationRun:
             self._saved = None
 
 
+#: score_calibration_set keeps the last CalibrationRun of a model -- with its captured CUDA graph and the graph's memory pool
+#: (~20 GB for a 512x1024 ResNet-101 micro-batch) -- so that the next call on the same model with the same settings skips
+#: capture.  Keyed by the model's identity AND the addresses of its parameters / buffers: a model whose tensors were
+#: re-allocated never sees a stale graph.  `release_cached_runs()` frees everything.
+_RUN_CACHE = {}
+
+
+def _run_key(model, *settings):
+    ptrs = tuple(t.data_ptr() for t in list(model.parameters()) + list(model.buffers()))
+    return settings + (hash(ptrs), len(ptrs))
+
+
+def release_cached_runs(model=None):
+    """Drops the cached CalibrationRun (CUDA graph + its memory pool) of `model`, or of every model."""
+    for k in [k for k in _RUN_CACHE if model is None or k == id(model)]:
+        ref, _, run = _RUN_CACHE.pop(k)
+        run.close()
+
+
+def release_cached_runs_by_id(mid):
+    entry = _RUN_CACHE.pop(mid, None)
+    if entry is not None:
+        entry[2]._graph, entry[2]._graph_grads = None, []
+
+
 def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0.999, restore_bn_stats=True, flush_bytes=1 << 30,
-                          return_class_stats=False, seed=0, scores_only=False, channels_last=True, fused=True):
+                          return_class_stats=False, seed=0, scores_only=False, channels_last=True, fused=True, n_images=None, graph=True):
     """Public end-to-end call: HOST images [n,3,H,W] / labels [n,H,W] -> EIC scores on the host.
+
+    `images` may also be a callable `fetch(lo, hi) -> (x [hi-lo,3,H,W], y [hi-lo,H,W])` returning host tensors for the global
+    image range [lo, hi) -- a loader for calibration sets that do not fit in host memory at once (then `labels` is ignored
+    and `n_images` gives the size of the set).
 
     Every step copies its micro-batch host->device from pinned memory and reads the step's loss back;
     with torch.distributed initialised the micro-batches are dealt round-robin (`shard_plan`).  Returns
@@ -606,9 +752,29 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     world = torch.distributed.get_world_size() if dist_on else 1
     rank = torch.distributed.get_rank() if dist_on else 0
-    plan = shard_plan(images.shape[0], micro_batch, world, rank)
-    run = CalibrationRun(model, num_classes, r=r, restore_bn_stats=restore_bn_stats, flush_bytes=flush_bytes,
-                         keep_totals=return_class_stats, seed=seed, scores_only=scores_only, fused=fused)
+    fetch = images if callable(images) else None
+    if fetch is not None:
+        if n_images is None:
+            raise ValueError("score_calibration_set: n_images is required when `images` is a loader")
+        x0, y0 = fetch(0, micro_batch)
+        img_shape, img_dtype, lab_shape, lab_dtype = tuple(x0.shape[1:]), x0.dtype, tuple(y0.shape[1:]), y0.dtype
+    else:
+        n_images = images.shape[0]
+        img_shape, img_dtype, lab_shape, lab_dtype = tuple(images.shape[1:]), images.dtype, tuple(labels.shape[1:]), labels.dtype
+    plan = shard_plan(n_images, micro_batch, world, rank)
+    key = _run_key(model, int(num_classes), micro_batch, float(r), bool(restore_bn_stats), int(flush_bytes), bool(return_class_stats),
+                   seed, bool(scores_only), bool(fused), world, img_shape, lab_shape, str(img_dtype), str(lab_dtype))
+    cached = _RUN_CACHE.pop(id(model), None) if graph else None
+    run = None
+    if cached is not None:
+        if cached[0]() is model and cached[1] == key and cached[2].closed:
+            run = cached[2]
+            run.reopen()
+        else:
+            cached[2].close()
+    if run is None:
+        run = CalibrationRun(model, num_classes, r=r, restore_bn_stats=restore_bn_stats, flush_bytes=flush_bytes,
+                             keep_totals=return_class_stats, seed=seed, scores_only=scores_only, fused=fused, graph=graph)
     h2d = d2h = 0
     losses = torch.empty(max(len(plan), 1), dtype=torch.float32).pin_memory()
     launches0 = ops.launch_count()
@@ -618,8 +784,8 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
         # fenced by events, keep the caching allocator out of it (per-step cross-stream allocations made it re-grow).
         copy_stream = torch.cuda.Stream(device=device)
         main_stream = torch.cuda.current_stream(device)
-        stage = [(torch.empty((micro_batch,) + tuple(images.shape[1:]), dtype=images.dtype, device=device),
-                  torch.empty((micro_batch,) + tuple(labels.shape[1:]), dtype=labels.dtype, device=device)) for _ in range(2)]
+        stage = [(torch.empty((micro_batch,) + img_shape, dtype=img_dtype, device=device),
+                  torch.empty((micro_batch,) + lab_shape, dtype=lab_dtype, device=device)) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
         pinned = [None, None]
@@ -627,7 +793,7 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
         def upload(step):
             lo, hi = plan[step]
             b = step & 1
-            xb, yb = images[lo:hi], labels[lo:hi]
+            xb, yb = fetch(lo, hi) if fetch is not None else (images[lo:hi], labels[lo:hi])
             if not xb.is_pinned():
                 xb, yb = xb.pin_memory(), yb.pin_memory()
             pinned[b] = (xb, yb)  # keep the pinned source alive until the copy has run
@@ -656,7 +822,12 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
         if return_class_stats:
             run.scorer.all_reduce_totals()
     finally:
-        run.close()
+        keep = bool(graph) and run._graph is not None and not converted
+        run.close(keep_graph=keep)
+        if keep:
+            import weakref
+            mid = id(model)
+            _RUN_CACHE[mid] = (weakref.ref(model, lambda _r, mid=mid: release_cached_runs_by_id(mid)), key, run)
         if converted:
             model.to(memory_format=torch.contiguous_format)
     sc = run.scorer

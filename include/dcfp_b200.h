@@ -185,7 +185,7 @@ int dcfp_class_balance_weights(const void* label, int label_dtype, int N, int H,
  *             dz*xhat, S2 += (dz*xhat)^2 -- the SAME class rows dcfp_class_stats' backward functor fills,
  *             so sum_k S1 == dgamma;  dgamma, dbeta (fp32 [C]);  dx = gamma*invstd*(dz - dbeta/M -
  *             xhat*dgamma/M) unless dx == NULL.  (x, dy) are read once for all sums, once more for dx.
- * `scratch`: caller-provided device buffer of dcfp_bn_scratch_bytes(C) bytes, 8-byte aligned, ZERO on entry
+ * `scratch`: caller-provided device buffer of dcfp_bn_scratch_bytes(C) bytes, 16-byte aligned, ZERO on entry
  * (fp64 partial sums striped against same-address atomic contention + the coefficient vectors the reduction
  * pass leaves for the element-wise pass + a ticket counter); one scratch per call in flight.            */
 typedef struct dcfp_bn_desc {

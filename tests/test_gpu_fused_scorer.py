@@ -57,7 +57,7 @@ def _arbiter_grads(model, classes, step):
     x, y = _batch([2 * step, 2 * step + 1], classes)
     out = arb(x.double(), y.long(), deepsup=True)
     (out["loss"] if isinstance(out, dict) else out).backward()
-    return float(out["loss"]), {n: p.grad.detach().clone() for n, p in arb.named_parameters() if p.grad is not None}
+    return float(out["loss"].detach()), {n: p.grad.detach().clone() for n, p in arb.named_parameters() if p.grad is not None}
 
 
 @pytest.mark.parametrize("arch,classes", [("deeplabv3", 19), ("psp", 150), ("deeplabv3p", 171)])
@@ -103,7 +103,8 @@ def test_which_layers_fuse_with_their_relu(native):
     ra = info["relu_after"]
     assert ra.get("backbone.layer1.0.bn1") and ra.get("backbone.layer1.0.bn2") and ra.get("backbone.bn1")
     assert "backbone.layer1.0.bn3" not in ra and "backbone.layer1.0.downsample.1" not in ra  # residual add comes first
-    assert ra.get("aspp.aspp1.bn") and ra.get("aspp.bn1")
+    assert ra.get("aspp.aspp1.bn") and ra.get("last_conv.1")
+    assert "aspp.bn1" not in ra  # in ignore_prune_layer: not scored, so it stays torch's BatchNorm
 
 
 def test_row_sums_are_the_gradient_autograd_hands_out(native):
@@ -118,16 +119,53 @@ def test_row_sums_are_the_gradient_autograd_hands_out(native):
     x, y = _batch([4, 5])
     sc.set_labels(y)
     model.zero_grad(set_to_none=True)
-    out = model(x, y, deepsup=True)
+    out = model(x, y.long(), deepsup=True)  # noqa
     (out["loss"] if isinstance(out, dict) else out).backward()
     sc.flush()
     rows = sc.step_arena[0].sum(0).cpu().numpy()
     grads = torch.cat([m.weight.grad.reshape(-1) for _, m in sc.layers]).cpu().numpy()
     mass = sc.step_arena[0].abs().sum(0).cpu().numpy()
-    assert (np.abs(rows - grads) <= 1e-6 * mass + 1e-12).all()
-    fused = [n for n, m in sc.layers if "forward" in m.__dict__]
-    assert len(fused) >= 60
+    # fused layers: rows and gradient come out of ONE kernel (fp64 totals rounded once).  The few maps the fused path does
+    # not take (1x1 pooled maps) keep torch's BN: there the gradient is cuDNN's own fp32 reduction (SURVEY app. C form)
+    fused = np.concatenate([np.full(m.weight.numel(), "forward" in m.__dict__ and m.weight.numel() % 4 == 0) for _, m in sc.layers])
+    big = np.concatenate([np.full(m.weight.numel(), n != "aspp.global_avg_pool.2") for n, m in sc.layers])
+    err = np.abs(rows - grads)
+    assert (err[fused & big] <= 1e-6 * mass[fused & big] + 1e-12).all()
+    assert (err[~(fused & big)] <= 2e-4 * np.abs(grads[~(fused & big)]) + 2e-4 * np.abs(grads).mean()).all()
+    assert sum("forward" in m.__dict__ for _, m in sc.layers) >= 60
     run.close()
+
+
+def test_graph_replay_equals_eager_launches(native):
+    """The third step of a shape is captured into a CUDA graph and replayed from then on: same kernels, same results as
+    launching them eagerly; a cached run (score_calibration_set) replays on its first step."""
+    from dcfp_b200 import scorer
+    from dcfp_b200.scorer import CalibrationRun, score_calibration_set
+    model = _model(seed=3)
+    res = {}
+    for graph in (False, True):
+        run = CalibrationRun(model, K, r=0.999, seed=2, fused=True, graph=graph)
+        losses = []
+        for s in range(5):
+            x, y = _batch([2 * (s % 2), 2 * (s % 2) + 1])
+            losses.append(float(run.step(x, y, mb_index=s)))
+        res[graph] = (losses, run.scorer.eic.cpu().numpy().copy(), run.scorer.totals.cpu().clone(), run.graph_replays)
+        run.close()
+    assert res[False][3] == 0 and res[True][3] == 3
+    assert np.allclose(res[False][0], res[True][0], rtol=1e-6)
+    rel = np.abs(res[True][1] - res[False][1]) / (np.abs(res[False][1]) + 0.1 * np.abs(res[False][1]).mean())
+    assert np.quantile(rel, 0.5) < 1e-3 and (rel < 0.5).mean() > 0.98, np.quantile(rel, [0.5, 0.9, 0.99])  # cuDNN atomics, noise-like gradients
+    # the run cache: second call on the same model skips capture and gives the same scores as the first
+    from dcfp_b200.workloads.synthetic import synthetic_batch
+    xs, ys = synthetic_batch(list(range(8)), K, H, W)
+    a = score_calibration_set(model, xs, ys, K, seed=0)
+    assert id(model) in scorer._RUN_CACHE
+    b = score_calibration_set(model, xs, ys, K, seed=0)
+    ea, eb = np.concatenate([v.numpy() for v in a["eic"].values()]), np.concatenate([v.numpy() for v in b["eic"].values()])
+    rel = np.abs(ea - eb) / (np.abs(ea) + 0.1 * np.abs(ea).mean())
+    assert np.quantile(rel, 0.5) < 1e-3 and (rel < 0.5).mean() > 0.98
+    scorer.release_cached_runs()
+    assert not scorer._RUN_CACHE and not any("forward" in m.__dict__ for m in model.modules())
 
 
 def test_eval_mode_and_no_grad_fall_back_to_torch(native):
