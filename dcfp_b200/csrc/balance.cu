@@ -52,8 +52,12 @@ __global__ void __launch_bounds__(256) balance_weight_kernel(const void* __restr
   const long long* cnt = counts + static_cast<long long>(n) * (K + 1);
   double numer = 1.0;
   if (mode == 2) {
+    // a class outside [0, K] cannot index the count table: it is treated as a class without pixels (numer = 1e-8); the
+    // reference (numpy fancy indexing, datasets/Base.py:84) raises IndexError there -- a kernel cannot, and the host does not
+    // read device data back to validate it
     const int cls = sample_class[n];
-    numer = 1.0 + 1e-8 - pow(beta, static_cast<double>(cnt[cls]));
+    const double c_cls = (cls >= 0 && cls <= K) ? static_cast<double>(cnt[cls]) : 0.0;
+    numer = 1.0 + 1e-8 - pow(beta, c_cls);
   }
   for (int k = threadIdx.x; k <= K; k += blockDim.x) {
     double w = 0.0;  // the ignore bin (k == K) maps to weight 0 (Base.py:84)

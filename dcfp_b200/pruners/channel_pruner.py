@@ -167,7 +167,8 @@ class ChannelPruner:
         try:
             ref_param = next(supernet.parameters())
             pseudo_img = torch.randn(*self.trace_input_size).to(device=ref_param.device, dtype=ref_param.dtype)
-            out = supernet.forward(pseudo_img, deepsup=True)
+            with torch.enable_grad():  # a caller's no_grad() must not yield an empty (and then cached) topology
+                out = supernet.forward(pseudo_img, deepsup=True)
             if isinstance(out, (list, tuple)):
                 loss = sum(o.sum() for o in out)
             elif isinstance(out, dict):
@@ -299,12 +300,15 @@ class ChannelPruner:
                 module2name[module] = name
         self.name2module, self.module2name = name2module, module2name
 
-        key = (type(supernet).__name__, tuple(self.trace_input_size), tuple(self.end_nodes),
-               tuple((n, type(m).__name__, tuple(m.weight.shape)) for n, m in name2module.items()))
+        cls = type(supernet)
+        key = (cls.__module__, cls.__qualname__, id(getattr(cls.forward, "__code__", None)), tuple(self.trace_input_size),
+               tuple(self.end_nodes), tuple((n, type(m).__name__, tuple(m.weight.shape)) for n, m in name2module.items()),
+               tuple(sorted((k, repr(v)) for k, v in vars(supernet).items() if isinstance(v, (bool, int, str)) and not k.startswith("_"))))
         topo = _TOPOLOGY_CACHE.get(key)
         if topo is None:
             topo = self._trace(supernet, name2module)
-            _TOPOLOGY_CACHE[key] = topo
+            if topo["links"]:  # never cache a trace that found nothing (the next call re-traces, like the reference)
+                _TOPOLOGY_CACHE[key] = topo
         else:
             # the reference traces every time and its pseudo image comes from the GLOBAL torch generator (:191); draw
             # the same numbers so that RNG-dependent callers (RandomChannelPruner) see the reference's stream

@@ -6,7 +6,7 @@ builder, but reproduce the reference's architectures exactly -- same module name
 (so `ignore_prune_layer`, `score.pth` keys and `channel_cfg` keys agree), same
 parameter-creation order (so `torch.manual_seed(s)` + default init yields bit-identical
 weights) and the same op order in `forward` (bit-identical CPU outputs).
-`tests/test_workload_nets.py` checks all three against the unmodified reference.
+`tests/test_reference_live_cpu.py::test_workload_nets_equal_reference` checks all three against the unmodified reference.
 
 Architectures (reference file:line):
   dilated ResNet-50/101/152, 3-conv stem, multi-grid layer4   networks/backbone/resnet.py:60-187

@@ -11,8 +11,15 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in _host;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
- *   - functions are re-entrant, hold no global state, never allocate device memory and never
- *     synchronise the device or the stream (hooks call them from the autograd engine thread);
+ *   - functions are re-entrant and thread-safe (hooks call them from the autograd engine thread).  They never
+ *     allocate device memory and never synchronise the device.  Process-wide state is limited to a launch counter
+ *     (dcfp_launch_count: statistics only) and a mutex-guarded record of which kernels already had their
+ *     shared-memory limit raised (cudaFuncSetAttribute, once per kernel and device).  Host-side work per call:
+ *     argument validation, cuTensorMapEncodeTiled for the TMA kernels (up to 2 maps per layer, host only), and --
+ *     dcfp_channel_gather_grouped only -- one cudaMemcpyAsync of the descriptor table from a pageable host staging
+ *     array (the runtime copies pageable memory before returning: no device synchronisation, but not asynchronous
+ *     to the host).  The cooperative one-launch BN forward (workspace != NULL) needs all its CTAs co-resident and
+ *     is launched with cudaLaunchCooperativeKernel;
  *   - return 0 on success, a negative DCFP_E* validation code, or a positive cudaError_t;
  *     no C++ exception crosses the boundary; dcfp_last_error() returns a thread-local message.
  */
@@ -167,7 +174,8 @@ int dcfp_bias_comp(const float* W, int O, int I, int khw, const float* act, floa
  * class_num[n][k] (k < K; bin K = ignore label) = per-image pixel counts; weight[n][p] (float64, as numpy) =
  * clip(w[label], 0, 1) with w = 1/(class_num+1) (mode 1) or the effective-number ratio
  * (1 + 1e-8 - beta^class_num[sample_class[n]]) / (1 + 1e-8 - beta^class_num[k]) (mode 2); ignored pixels get 0.
- * class_num: device [N][K+1] int64 (overwritten); sample_class: device [N] int32 (mode 2) or NULL.            */
+ * class_num: device [N][K+1] int64 (overwritten); sample_class: device [N] int32 (mode 2) or NULL; a sample_class outside
+ * [0, K] is treated as a class without pixels (the reference raises IndexError there).                           */
 int dcfp_class_balance_weights(const void* label, int label_dtype, int N, int H, int W, int K, int ignore_label,
                                const int32_t* sample_class, int mode, double beta, int64_t* class_num, double* weight,
                                void* stream);

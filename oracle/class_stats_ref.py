@@ -16,7 +16,7 @@ def nearest_labels(label, h, w):
     """Index-math restatement of legacy `nearest`: src = min(floor(dst * (float32)(in/out)), in-1).
 
     Follows ATen's nearest_neighbor_compute_source_index (UpSample.h) -- the scale and the product
-    are float32.  tests/test_oracle.py checks it against F.interpolate itself.
+    are float32.  tests/test_oracle_golden.py::test_nearest_labels_matches_interpolate checks it against F.interpolate itself.
     """
     label = torch.as_tensor(label)
     n, h0, w0 = label.shape

@@ -221,7 +221,7 @@ NHWC_SHAPES = [
     (3, 128, 31, 37, 250, 300, 19),     # ragged: n_px not a multiple of the group / chunk
     (2, 100, 20, 20, 160, 160, 19),     # C % 4 == 0 but not a multiple of the slab
     (2, 66, 20, 20, 160, 160, 19),      # C % 4 != 0 -> generic path
-    (2, 128, 32, 32, 256, 256, 150),    # K too large for the per-warp tables -> generic path
+    (2, 128, 32, 32, 256, 256, 150),    # K = 150 > 12 slot rows: tagged slot cache with evictions (any K <= 255 stays on the TMA path)
     (2, 512, 2, 2, 512, 512, 19),       # tiny pooled map -> generic path
 ]
 

@@ -9,8 +9,8 @@ at these sizes, so it is not run here:
   * Cauchy-Schwarz per (class, channel): S1^2 <= cnt * S2;
   * additivity over micro-batches: totals(A then B) == totals(A) + totals(B).
 
-Tolerances: sums of up to 2.6e5 fp32 terms in different orders (cuDNN's reduction vs K1's fp32-in-CTA / fp64-across-CTA),
-and cuDNN's backward is not bit-reproducible run to run: 1e-3 relative to the layer's mean magnitude."""
+Tolerances: written at each check.  Row sums vs the gradient: 1e-5 of the mass for the fused layers; the additivity check
+compares RUNS, and cuDNN's convolution backward is not bit-reproducible run to run (1e-3 of the second-moment mass)."""
 import numpy as np
 import pytest
 import torch
@@ -69,11 +69,18 @@ def test_full_size_properties(native, cfg):
     S1, S2 = ta["S"][0], ta["S"][1]  # [K + 1, sum C] fp64: the classes, then the pixels outside [0, K) (ignore label)
     assert S1.shape == (K + 1, ta["offsets"][-1])
 
-    # class sums add up to autograd's gradient of every BN gamma
+    # class sums add up to the gradient of every BN gamma that autograd hands out.  The scored layers run on the fused BN
+    # kernels here (channels_last): rows and gradient come out of ONE kernel, different fp32 partial groupings -> 1e-5 of
+    # the mass sum|v| (bounded through Cauchy-Schwarz by sqrt(pixels * S2)).  The few maps the fused path does not take
+    # (1x1 / 2x2 / 3x3 / 6x6 pools) keep cuDNN's BN: its fp32 gradient is compared in SURVEY app. C's form at 2e-4
+    # (tests/test_gpu_arbiter.py measures both against an fp64 arbiter on the same device tensors).
     dgamma = S1.sum(0)
+    n_px = 2.0 * c["height"] * c["width"]
     for name, a, b, g in zip(ta["names"], ta["offsets"][:-1], ta["offsets"][1:], ta["grads"]):
-        tol = 1e-3 * np.abs(g) + 1e-3 * np.abs(g).mean()
-        bad = np.abs(dgamma[a:b] - g) > tol
+        mass_ub = np.sqrt(n_px * S2[:, a:b].sum(0))
+        tol = np.minimum(1e-5 * mass_ub, 1e-3 * np.abs(g) + 1e-3 * np.abs(g).mean()) + 2e-4 * np.abs(g) * (mass_ub < 1e-30)
+        tol = np.maximum(tol, 2e-4 * np.abs(g) + 2e-4 * np.abs(g).mean()) if ("pool" in name or "stages" in name) else tol
+        bad = np.abs(dgamma[a:b] - g) > tol + 1e-30
         assert not bad.any(), "%s: %d / %d channels off, worst %.3g" % (name, bad.sum(), b - a, np.abs(dgamma[a:b] - g).max())
     # EIC bit-exact given those gradients (first step: eic = flag * |g| * (1 - r))
     exp = eic_ref.eic_step(0, dgamma.astype(np.float32), ta["gamma"], 0.999)
