@@ -44,8 +44,9 @@ def compare_masks(score_a, score_b, layer_off, layer_group, global_percent):
     """Masks of two score vectors for the same layers (thresholds per vector; the min-keep fallback is left out: it only
     adds channels).  Returns dict(flipped, n, flip_band, disc_near, margins_a, margins_b):
       flipped    channels whose keep bit differs
-      flip_band  max over the flipped channels of |score - thresh| / thresh in either vector (0 if none): every flip must
-                 sit inside the band the score discrepancy explains
+      flip_band  max over the flipped channels of min_{a,b} |score - thresh| / thresh (0 if none): a channel whose keep bit
+                 differs sits, in at least one of the two vectors, this close to its threshold -- it must be inside the
+                 band the score discrepancy explains
       disc_near  max relative discrepancy |a - b| / max(a, b) over the channels within 10 % of a threshold."""
     a, b = np.asarray(score_a, dtype=np.float32), np.asarray(score_b, dtype=np.float32)
     ma, mb = threshold_margins(a, layer_off, layer_group, global_percent), threshold_margins(b, layer_off, layer_group, global_percent)
@@ -59,7 +60,7 @@ def compare_masks(score_a, score_b, layer_off, layer_group, global_percent):
         f = ka != kb
         flipped += int(f.sum())
         if f.any():
-            band = max(band, float(np.maximum(da[f], db[f]).max()))
+            band = max(band, float(np.minimum(da[f], db[f]).max()))
         near = (da < 0.1) | (db < 0.1)
         if near.any():
             disc = max(disc, float((np.abs(va - vb)[near] / np.maximum(np.maximum(va, vb)[near], 1e-38)).max()))
