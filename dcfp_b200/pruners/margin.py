@@ -35,8 +35,11 @@ def threshold_margins(score, layer_off, layer_group, global_percent):
         below = float(lo[-1]) if lo.size else float("nan")
         above = float(hi[0]) if hi.size else float("nan")
         gaps = [x for x in (float(t) - below, above - float(t)) if x == x]
-        denom = max(abs(float(t)), np.finfo(np.float32).tiny)
-        res[g] = dict(thresh=float(t), below=below, above=above, margin=(min(gaps) / denom) if gaps else float("inf"))
+        # thresh == 0 (after few steps half of the scores are exactly 0: the gate failed every time) has no relative margin:
+        # every zero score is pruned together, the margin is the absolute gap to the smallest positive score
+        rel = float(t) != 0.0
+        res[g] = dict(thresh=float(t), below=below, above=above, relative=rel,
+                      margin=((min(gaps) / abs(float(t))) if rel else min(gaps)) if gaps else float("inf"))
     return res
 
 
@@ -68,4 +71,5 @@ def compare_masks(score_a, score_b, layer_off, layer_group, global_percent):
 
 
 def format_margins(m):
-    return ", ".join("group %d: thresh %.6g, margin %.3g" % (g, v["thresh"], v["margin"]) for g, v in sorted(m.items()))
+    return ", ".join("group %d: thresh %.6g, margin %.3g%s" % (g, v["thresh"], v["margin"], "" if v.get("relative", True) else " (absolute: thresh is 0)")
+                     for g, v in sorted(m.items()))

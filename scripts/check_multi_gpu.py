@@ -20,8 +20,9 @@ from dcfp_b200.scorer import CalibrationRun, score_calibration_set, shard_plan
 from dcfp_b200.workloads.segnets import build_segnet
 from dcfp_b200.workloads.synthetic import synthetic_batch
 
-K, H, W, MB, N_IMG = 19, 256, 512, 2, 16
+K, H, W, MB = 19, 256, 512, 2
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+N_IMG = max(16, 4 * MB * world)  # at least 4 steps at every world size (after one step half of the scores are exactly 0)
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
