@@ -30,7 +30,7 @@ class BnDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("x", "y", "dy", "dx", "gamma", "beta", "mean", "invstd", "running_mean", "running_var",
                                                "scratch", "keys", "S1", "S2", "dgamma", "dbeta")] + \
                [(n, ctypes.c_int32) for n in ("N", "C", "h", "w", "dtype", "relu", "K", "ld")] + \
-               [("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("phases", ctypes.c_int32), ("reserved", ctypes.c_int32),
+               [("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("phases", ctypes.c_int32), ("arena_f32", ctypes.c_int32),
                 ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64)]
 
 
@@ -76,6 +76,7 @@ def load(path=LIB_PATH):
     lib.dcfp_eic_update_flat.argtypes = [vp, vp, vp, i32, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_reduce_classes.argtypes = [vp, i32, i32, vp, vp]
     lib.dcfp_fold_step.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.dcfp_fold_step2.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.dcfp_thresh_mask.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.POINTER(i64), vp, vp, vp, vp]
     lib.dcfp_channel_gather.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp]
     lib.dcfp_channel_gather_workspace.restype = ctypes.c_size_t

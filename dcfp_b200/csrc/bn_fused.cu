@@ -27,7 +27,7 @@
 namespace dcfp {
 
 // class_stats.cu
-int k1_run_bn_backward(const dcfp_layer_desc& d, const BnFinal& fin, bool relu, cudaStream_t stream);
+int k1_run_bn_backward(const dcfp_layer_desc& d, const BnFinal& fin, bool relu, float* S1f, float* S2f, cudaStream_t stream);
 
 namespace {
 
@@ -282,7 +282,8 @@ int validate_bn(const dcfp_bn_desc* d, bool backward) {
                DCFP_EUNSUPPORTED, "bn: gamma / beta / mean / invstd must be 16-byte aligned");
   DCFP_REQUIRE(d->N > 0 && d->C > 0 && d->h > 0 && d->w > 0, DCFP_EINVAL, "bn: bad extent N=%d C=%d h=%d w=%d", d->N, d->C, d->h, d->w);
   DCFP_REQUIRE(d->dtype == DCFP_F32 || d->dtype == DCFP_BF16, DCFP_EINVAL, "bn: unknown dtype %d", d->dtype);
-  DCFP_REQUIRE(d->phases >= 0 && d->phases <= 2 && d->reserved == 0, DCFP_EINVAL, "bn: bad phases (%d) / reserved field", d->phases);
+  DCFP_REQUIRE(d->phases >= 0 && d->phases <= 2 && (d->arena_f32 == 0 || d->arena_f32 == 1), DCFP_EINVAL,
+               "bn: bad phases (%d) / arena_f32 (%d)", d->phases, d->arena_f32);
   const int kch = d->dtype == DCFP_F32 ? 4 : 8;
   DCFP_REQUIRE(d->C % kch == 0, DCFP_EUNSUPPORTED, "bn: C=%d must be a multiple of %d (16-byte channel vectors)", d->C, kch);
   DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->x) % 16 == 0, DCFP_EUNSUPPORTED, "bn: x must be 16-byte aligned");
@@ -429,12 +430,14 @@ extern "C" int dcfp_bn_backward(const dcfp_bn_desc* d, void* stream_) {
     L.affine_mode = DCFP_AFFINE_INVSTD_MEAN;
     L.keys = d->keys;
     L.K = d->K;
-    L.S1 = d->S1, L.S2 = d->S2;
+    L.S1 = static_cast<double*>(d->S1), L.S2 = static_cast<double*>(d->S2);
     L.ld = d->ld > 0 ? d->ld : d->C;
     // the dx pass re-reads (x, dy): keep them in the 126 MB L2 when the pair can fit
     const long long bytes = 2LL * d->N * d->C * d->h * d->w * (d->dtype == DCFP_F32 ? 4 : 2);
     L.hints = ((d->dx != nullptr || d->phases == 1) && bytes <= (96LL << 20)) ? DCFP_HINT_KEEP_L2 : 0;
-    rc = k1_run_bn_backward(L, final_args(d), d->relu != 0, stream);  // B1 (+ finalisation by its last CTA)
+    float* S1f = d->arena_f32 ? static_cast<float*>(d->S1) : nullptr;
+    float* S2f = d->arena_f32 ? static_cast<float*>(d->S2) : nullptr;
+    rc = k1_run_bn_backward(L, final_args(d), d->relu != 0, S1f, S2f, stream);  // B1
     if (rc || d->phases == 1) return rc;
   }
   return d->dtype == DCFP_F32 ? backward_dx_t<float>(d, stream) : backward_dx_t<__nv_bfloat16>(d, stream);

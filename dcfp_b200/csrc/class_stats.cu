@@ -231,7 +231,15 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
 // ---- internal entry points used by bn_fused.cu ---------------------------------------------------------------------
 // BN backward, first pass: class-keyed S1/S2 of v = dz * xhat, the per-channel totals (sum dz, sum dz * xhat) into the
 // scratch stripes, and -- by the last CTA -- dgamma / dbeta and the dx coefficients (bn_common.cuh)
-int k1_run_bn_backward(const dcfp_layer_desc& d, const BnFinal& fin, bool relu, cudaStream_t stream) {
+int k1_run_bn_backward(const dcfp_layer_desc& d0, const BnFinal& fin, bool relu, float* S1f, float* S2f, cudaStream_t stream) {
+  dcfp_layer_desc d = d0;
+  if (S1f != nullptr) {  // fp32 rows: the fp64 pointers are unused (validate() wants them non-null)
+    DCFP_REQUIRE(S2f != nullptr && reinterpret_cast<uintptr_t>(S1f) % 16 == 0 && reinterpret_cast<uintptr_t>(S2f) % 16 == 0 &&
+                     (d.ld > 0 ? d.ld : d.C) % 4 == 0,
+                 DCFP_EINVAL, "bn_backward: fp32 class rows need 16-byte aligned S1 / S2 and ld %% 4 == 0");
+    d.S1 = reinterpret_cast<double*>(S1f);
+    d.S2 = reinterpret_cast<double*>(S2f);
+  }
   int rc = validate(d, 0);
   if (rc) return rc;
   DCFP_REQUIRE(d.dy != nullptr && d.affine_mode == DCFP_AFFINE_INVSTD_MEAN && nhwc_ok(d), DCFP_EUNSUPPORTED,
@@ -240,7 +248,7 @@ int k1_run_bn_backward(const dcfp_layer_desc& d, const BnFinal& fin, bool relu, 
   NhwcPlan plan;
   plan.single_wave = true;
   plan.keep_l2 = (d.hints & DCFP_HINT_KEEP_L2) != 0;
-  const NhwcFused F{fin.gamma, fin.beta, fin};
+  const NhwcFused F{fin.gamma, fin.beta, fin, S1f, S2f};
   const int which = 0;
   if (d.dtype == DCFP_F32)
     return relu ? run_nhwc<float, true, kSmallGroup, 2>(&d, &which, 1, plan, stream, &F)

@@ -54,22 +54,31 @@ __global__ void reduce_classes_kernel(const double* __restrict__ S1, int K, int 
   out[c] = static_cast<float>(s);
 }
 
-// end-of-step fold: dgamma = sum_k step.S1, total += step, step = 0  (one coalesced pass, thread == channel)
-__global__ void fold_step_kernel(double* __restrict__ step, double* __restrict__ total, int K, int C, float* __restrict__ dgamma) {
+// end-of-step fold: dgamma = sum_k step.S1, total += step, step = 0  (one coalesced pass, thread == channel).
+// step32 (optional): the fp32 per-step arena the fused BN backward fills with vector atomics; same layout, folded in fp64.
+__global__ void fold_step_kernel(double* __restrict__ step, float* __restrict__ step32, double* __restrict__ total, int K, int C,
+                                 float* __restrict__ dgamma) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const size_t plane = static_cast<size_t>(K) * C;
   double s = 0.0;
   for (int k = 0; k < K; ++k) {
     const size_t o = static_cast<size_t>(k) * C + c;
-    const double a = step[o], b = step[plane + o];
+    double a = step[o], b = step[plane + o];
+    if (a != 0.0) step[o] = 0.0;
+    if (b != 0.0) step[plane + o] = 0.0;
+    if (step32 != nullptr) {
+      const float a32 = step32[o], b32 = step32[plane + o];
+      if (a32 != 0.f) step32[o] = 0.f;
+      if (b32 != 0.f) step32[plane + o] = 0.f;
+      a += static_cast<double>(a32);
+      b += static_cast<double>(b32);
+    }
     s += a;
     if (total != nullptr) {
       if (a != 0.0) total[o] += a;
       if (b != 0.0) total[plane + o] += b;
     }
-    if (a != 0.0) step[o] = 0.0;
-    if (b != 0.0) step[plane + o] = 0.0;
   }
   if (dgamma != nullptr) dgamma[c] = static_cast<float>(s);
 }
@@ -322,11 +331,15 @@ extern "C" int dcfp_reduce_classes(const double* S1, int K, int C, float* out, v
   return finish_launch("reduce_classes");
 }
 
-extern "C" int dcfp_fold_step(double* step, double* total, int K, int C, float* dgamma, void* stream) {
+extern "C" int dcfp_fold_step2(double* step, float* step32, double* total, int K, int C, float* dgamma, void* stream) {
   DCFP_REQUIRE(step != nullptr, DCFP_EINVAL, "fold_step: null step arena");
   DCFP_REQUIRE(K > 0 && C > 0, DCFP_EINVAL, "fold_step: K=%d C=%d", K, C);
-  fold_step_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(step, total, K, C, dgamma);
+  fold_step_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(step, step32, total, K, C, dgamma);
   return finish_launch("fold_step");
+}
+
+extern "C" int dcfp_fold_step(double* step, double* total, int K, int C, float* dgamma, void* stream) {
+  return dcfp_fold_step2(step, nullptr, total, K, C, dgamma, stream);
 }
 
 extern "C" int dcfp_thresh_mask(const float* score, const int32_t* layer_off, const int32_t* layer_group, const int32_t* min_keep,

@@ -71,6 +71,8 @@ struct NhwcFused {
   const float* gamma;  // [C]  z = fma(x, zs, zt) with zs = gamma * invstd, zt = fma(-mean, zs, beta): the SAME fp32
   const float* beta;   // [C]  expressions the forward evaluated, so the gate equals "forward output > 0" bit for bit
   BnFinal fin;         // scratch (totals go to its stripes) + what the last CTA needs to finalise the backward
+  float* S1f;          // non-null: the class rows go to this fp32 arena with 128-bit vector reductions instead of L.S1 / L.S2
+  float* S2f;
 };
 constexpr int kNhwcBigGroupFwd = 128;  // 128 * (128 + 72) B = 25.0 KB of kernel parameters
 constexpr int kNhwcBigGroupBwd = 80;   //  80 * (256 + 72) B = 25.6 KB
@@ -164,7 +166,15 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       b.z += __shfl_xor_sync(0xffffffffu, b.z, 16);
       b.w += __shfl_xor_sync(0xffffffffu, b.w, 16);
     }
-    if (lane_on && !(fold2 && lane >= 16) && !P.debug_skip_rows) {
+    if (FUSED && F.S1f != nullptr) {
+      if (lane_on && !(fold2 && lane >= 16) && !P.debug_skip_rows) {
+        const size_t o = cls * ld + static_cast<size_t>(c0);
+        if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)
+          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(F.S1f + o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+        if (b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f)
+          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(F.S2f + o), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+      }
+    } else if (lane_on && !(fold2 && lane >= 16) && !P.debug_skip_rows) {
       double* d1 = out1 + cls * ld;
       double* d2 = out2 + cls * ld;
       if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));

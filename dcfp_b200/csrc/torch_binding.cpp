@@ -160,8 +160,8 @@ Tensor reduce_classes(const Tensor& S1) {
   return out;
 }
 
-// step / total: fp64 [2, K, C]; returns dgamma fp32 [C]
-Tensor fold_step(Tensor step, const optional<Tensor>& total) {
+// step / total: fp64 [2, K, C]; step32: optional fp32 [2, K, C]; returns dgamma fp32 [C]
+Tensor fold_step(Tensor step, const optional<Tensor>& total, const optional<Tensor>& step32) {
   require_cuda(step, "step");
   TORCH_CHECK(step.scalar_type() == at::kDouble && step.is_contiguous() && step.dim() == 3 && step.size(0) == 2,
               "dcfp::fold_step: step must be a contiguous fp64 [2,K,C] arena");
@@ -172,10 +172,17 @@ Tensor fold_step(Tensor step, const optional<Tensor>& total) {
                 "dcfp::fold_step: total must match step");
     tp = total->data_ptr<double>();
   }
+  float* sp = nullptr;
+  if (step32.has_value()) {
+    require_cuda(*step32, "step32");
+    TORCH_CHECK(step32->scalar_type() == at::kFloat && step32->is_contiguous() && step32->sizes() == step.sizes(),
+                "dcfp::fold_step: step32 must be a contiguous fp32 tensor of step's shape");
+    sp = step32->data_ptr<float>();
+  }
   Tensor out = at::empty({step.size(2)}, step.options().dtype(at::kFloat));
   c10::cuda::CUDAGuard guard(step.device());
-  check_rc(dcfp_fold_step(step.data_ptr<double>(), tp, static_cast<int>(step.size(1)), static_cast<int>(step.size(2)),
-                          out.data_ptr<float>(), cur_stream()),
+  check_rc(dcfp_fold_step2(step.data_ptr<double>(), sp, tp, static_cast<int>(step.size(1)), static_cast<int>(step.size(2)),
+                           out.data_ptr<float>(), cur_stream()),
            "fold_step");
   return out;
 }
@@ -442,13 +449,32 @@ std::tuple<Tensor, Tensor, Tensor> bn_backward(const Tensor& x, const Tensor& dy
   TORCH_CHECK(dy.sizes() == x.sizes() && dy.scalar_type() == x.scalar_type() && dy.is_contiguous(at::MemoryFormat::ChannelsLast),
               "dcfp::bn_backward: dy must match x (shape, dtype, channels_last)");
   d.dy = dy.data_ptr();
-  // reuse the K1 descriptor checks for keys / S1 / S2
-  const dcfp_layer_desc L = make_desc(x, dy, invstd, mean, keys, S1, S2, K, DCFP_AFFINE_INVSTD_MEAN);
-  d.keys = L.keys;
-  d.S1 = L.S1;
-  d.S2 = L.S2;
+  if (S1.scalar_type() == at::kFloat) {  // fp32 per-step arena: vector reductions (dcfp_bn_desc.arena_f32)
+    require_cuda(S1, "S1");
+    require_cuda(S2, "S2");
+    TORCH_CHECK(S2.scalar_type() == at::kFloat && S1.dim() == 2 && S2.dim() == 2 && S1.size(0) == K && S2.size(0) == K &&
+                    S1.size(1) == x.size(1) && S2.size(1) == x.size(1) && S1.stride(1) == 1 && S2.stride(1) == 1 &&
+                    S1.stride(0) == S2.stride(0),
+                "dcfp::bn_backward: fp32 S1 / S2 must be [K, C] views with unit column stride and one row stride");
+    if (keys.has_value()) {
+      require_cuda(*keys, "keys");
+      TORCH_CHECK(keys->scalar_type() == at::kByte && keys->is_contiguous() && keys->dim() == 3 && keys->size(0) == x.size(0) &&
+                      keys->size(1) == x.size(2) && keys->size(2) == x.size(3), "dcfp::bn_backward: keys must be uint8 [N,h,w]");
+      d.keys = keys->data_ptr<uint8_t>();
+    }
+    d.S1 = S1.data_ptr<float>();
+    d.S2 = S2.data_ptr<float>();
+    d.ld = static_cast<int32_t>(K == 1 ? x.size(1) : S1.stride(0));
+    d.arena_f32 = 1;
+  } else {
+    // reuse the K1 descriptor checks for keys / S1 / S2
+    const dcfp_layer_desc L = make_desc(x, dy, invstd, mean, keys, S1, S2, K, DCFP_AFFINE_INVSTD_MEAN);
+    d.keys = L.keys;
+    d.S1 = L.S1;
+    d.S2 = L.S2;
+    d.ld = L.ld;
+  }
   d.K = static_cast<int32_t>(K);
-  d.ld = L.ld;
   Tensor dx = need_dx ? at::empty_like(x, x.options(), at::MemoryFormat::ChannelsLast) : at::empty({0}, x.options());
   Tensor dgamma = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
   Tensor dbeta = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
@@ -474,7 +500,7 @@ TORCH_LIBRARY(dcfp, m) {
       "Tensor(b!)[] S2s, int K, int affine_mode=0) -> ()",
       &class_stats_grouped);
   m.def("reduce_classes(Tensor S1) -> Tensor", &reduce_classes);
-  m.def("fold_step(Tensor(a!) step, Tensor(b!)? total) -> Tensor", &fold_step);
+  m.def("fold_step(Tensor(a!) step, Tensor(b!)? total, Tensor(c!)? step32=None) -> Tensor", &fold_step);
   m.def("eic_update(Tensor[] grads, Tensor[] gammas, Tensor offsets, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",
         &eic_update);
   m.def("eic_update_flat(Tensor grad, Tensor gamma, Tensor(a!) eic, float r, float one_minus_r, bool first_step) -> ()",

@@ -86,9 +86,10 @@ def class_stats_grouped(xs, keys, K, S1s, S2s, dys=None, scales=None, shifts=Non
                                list(S2s), int(K), int(affine_mode))
 
 
-def fold_step(step, total=None):
-    """dgamma[c] = sum_k step[0,k,c]; total += step; step = 0 -- one launch.  step/total: fp64 [2,K,C]."""
-    return load().fold_step(step, total)
+def fold_step(step, total=None, step32=None):
+    """dgamma[c] = sum_k step[0,k,c]; total += step; step = 0 -- one launch.  step/total: fp64 [2,K,C]; step32: optional
+    fp32 arena of the same shape (the fused BN backward's class rows), folded in and zeroed the same way."""
+    return load().fold_step(step, total, step32)
 
 
 def reduce_classes(S1):

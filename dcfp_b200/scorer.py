@@ -160,6 +160,12 @@ class ClassStatsScorer:
             raise ValueError("num_classes must be in [1, 254] (uint8 class keys, one more row for pixels outside [0, K))")
         R = self.rows = K + 1  # row K: pixels whose label is outside [0, K) (ignore label)
         self.step_arena = torch.zeros(2, R, C, dtype=torch.float64, device=self.device)
+        # fused BN layers write their class rows into an fp32 twin of the step arena with 128-bit vector reductions (a
+        # quarter of the atomic instructions); fp32 only across the CTAs of one launch: fold_step adds it to the fp64 totals
+        # and zeroes it every step.  Needs 16-byte aligned rows: sum C and every layer's column offset multiples of 4.
+        sizes_ = [m.weight.numel() for _, m in self.layers]
+        self.step_arena32 = torch.zeros(2, R, C, dtype=torch.float32, device=self.device) \
+            if (fused and mode == "bwd" and all(c % 4 == 0 for c in sizes_)) else None
         # pass-wide totals and pixel counts share one buffer: ONE all-reduce combines everything
         self.total_arena = torch.zeros(2 * R * C + MAX_RESOLUTIONS * K, dtype=torch.float64, device=self.device) if keep_totals else None
         self.totals = self.total_arena[:2 * R * C].view(2, R, C) if keep_totals else None
@@ -198,7 +204,10 @@ class ClassStatsScorer:
             import os
             if os.environ.get("DCFP_BN_COOP", "0") == "1":
                 self._bn_workspace = ops.bn_workspace(max(sizes), self.device)
-        self._fused_layers = {n: _FusedLayer(self, n, m, self._views[n][0], self._views[n][1], i)
+        self._views32 = {n: (self.step_arena32[0][:, a:b], self.step_arena32[1][:, a:b])
+                         for n, a, b in zip(self.names, self.offsets[:-1], self.offsets[1:])} if self.step_arena32 is not None else {}
+        rows_of = self._views32 if self.step_arena32 is not None else self._views
+        self._fused_layers = {n: _FusedLayer(self, n, m, rows_of[n][0], rows_of[n][1], i)
                               for i, (n, m) in enumerate(self.layers)} if self.fused else {}
         self._fused_calls = {}
         self._relu_after = {}  # bn name -> True once an in-place nn.ReLU was seen consuming that BN's output
@@ -470,7 +479,14 @@ class ClassStatsScorer:
         """End of one step: flush deferred layers, then ONE launch yields dgamma = sum_k S1 (fp32 [sumC]),
         adds the step arena into the pass totals and zeroes it for the next step."""
         self.flush()
-        return ops.fold_step(self.step_arena, self.totals)
+        return ops.fold_step(self.step_arena, self.totals, self.step_arena32)
+
+    def step_rows(self, name):
+        """(S1, S2) fp64 [K+1, C] of layer `name` accumulated since the last fold (hook-fed fp64 rows + fused fp32 rows)."""
+        a, b = self._views[name]
+        if name in self._views32:
+            a, b = a + self._views32[name][0].double(), b + self._views32[name][1].double()
+        return a, b
 
     def all_reduce_totals(self):
         """ONE collective for all layers, both moments and the pixel counts (SUM, fp64, NCCL over NVLink)."""
@@ -597,6 +613,8 @@ class CalibrationRun:
         sc.steps = 0
         sc.eic.zero_()
         sc.step_arena.zero_()
+        if sc.step_arena32 is not None:
+            sc.step_arena32.zero_()
         if sc.total_arena is not None:
             sc.total_arena.zero_()
         else:

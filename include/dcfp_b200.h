@@ -133,6 +133,9 @@ int dcfp_reduce_classes(const double* S1, int K, int C, float* out, void* stream
  * total[m][k][c] += step[m][k][c] for both moments m in {0,1};  step[m][k][c] = 0.
  * step / total: fp64 [2][K][C] (S1 rows then S2 rows).  total may be NULL (no pass-wide stats). */
 int dcfp_fold_step(double* step, double* total, int K, int C, float* dgamma, void* stream);
+/* Same with a second, fp32 per-step arena of the same shape (may be NULL): the fused BN backward fills it with vector
+ * atomics (dcfp_bn_desc.arena_f32); dgamma and total take step + step32 (summed in fp64), both are zeroed.       */
+int dcfp_fold_step2(double* step, float* step32, double* total, int K, int C, float* dgamma, void* stream);
 
 /* ---- K2b: global threshold + keep masks -- pruners/dcfp_pruner.py:43-92 ------------------------
  * score: concatenated fp32 scores of the n_layers scored layers; layer l owns
@@ -209,8 +212,8 @@ typedef struct dcfp_bn_desc {
   float* running_var;    /* [C] or NULL */
   void* scratch;         /* dcfp_bn_scratch_bytes(C) bytes, zero on entry */
   const uint8_t* keys;   /* backward: [N,h,w] class keys, or NULL (K == 1) */
-  double* S1;            /* backward: [K, ld] class rows */
-  double* S2;
+  void* S1;              /* backward: [K, ld] class rows, fp64 -- or fp32 when arena_f32 is set */
+  void* S2;
   float* dgamma;         /* backward out [C] */
   float* dbeta;          /* backward out [C] */
   int32_t N, C, h, w;
@@ -221,7 +224,10 @@ typedef struct dcfp_bn_desc {
   int32_t phases;        /* 0: the whole call; 1: only the reduction pass (sums, statistics / gradients of gamma and
                             beta [+ S1/S2]); 2: only the element-wise pass (needs the scratch a phase-1 call left) --
                             lets a caller time the two apart */
-  int32_t reserved;      /* must be 0 */
+  int32_t arena_f32;     /* backward: 1 = S1 / S2 are fp32 [K, ld] rows of a PER-STEP arena (zeroed every step by dcfp_fold_step2), 16-byte
+                            aligned with ld % 4 == 0: the class rows then leave a CTA as 128-bit vector reductions
+                            (red.global.v4.f32), a quarter of the atomic instructions of the fp64 form.  fp32 across the
+                            <= #SMs CTAs of ONE launch only; every cross-step / cross-rank sum stays fp64.  0 = fp64 rows */
   void* workspace;       /* forward: dcfp_bn_workspace_bytes(C) bytes of device scratch, NOT zeroed, reusable by every
                             call on the same stream (per-CTA partial sums of the one-launch forward); NULL selects the
                             two-launch forward */

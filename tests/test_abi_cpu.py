@@ -52,6 +52,7 @@ def test_validation_errors_do_not_touch_the_device(lib):
     assert lib.dcfp_label_keys(None, 0, 1, 1, 1, 1, 1, 19, None, None, None) == -1
     assert lib.dcfp_eic_update_flat(None, None, None, 4, 0.5, 0.5, 1, None) == -1
     assert lib.dcfp_fold_step(None, None, 19, 4, None, None) == -1
+    assert lib.dcfp_fold_step2(None, None, None, 19, 4, None, None) == -1
     k = (ctypes.c_int64 * 2)(5, 0)
     assert lib.dcfp_thresh_mask(0x1000, 0x1000, 0x1000, 0x1000, 1, 4, k, 0x1000, 0x1000, None, None) == -1  # k_idx >= n_total
     assert lib.dcfp_channel_gather(0x1000, 0x1000, None, 4, None, 3, 4, 1, 4, None) == -1  # in_idx NULL but n_in != I

@@ -113,7 +113,7 @@ def test_fused_bn_backward_against_fp64_arbiter(native):
         dz = dy * gate
         keys = sc._keys_for(xd.shape[2], xd.shape[3])
         rows, mass = _arbiter_rows(xd, dz, mean, invstd, keys, K + 1)
-        S1 = sc._views[n][0]
+        S1 = sc.step_rows(n)[0]
         e = (S1 - rows).abs()
         worst = max(worst, float((e / (mass + 1e-30)).max()))
         assert bool((e <= 1e-5 * mass + 1e-30).all()), "%s: fused class row off by %.3g of its mass" % (n, float((e / (mass + 1e-30)).max()))

@@ -94,7 +94,9 @@ def test_forward_matches_fp64_batch_norm(native, shape, relu, one_launch):
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("relu", [True, False])
-def test_backward_matches_fp64_autograd_and_class_rows(native, shape, relu):
+@pytest.mark.parametrize("arena", [torch.float64, torch.float32])
+def test_backward_matches_fp64_autograd_and_class_rows(native, shape, relu, arena):
+    """arena fp32: the per-step arena the scorer uses -- class rows leave a CTA as 128-bit vector reductions."""
     from dcfp_b200 import ops
     N, C, h, w, K = shape
     x, dy, gamma, beta = _inputs(N, C, h, w, seed=3 * C + w)
@@ -104,7 +106,7 @@ def test_backward_matches_fp64_autograd_and_class_rows(native, shape, relu):
     sums = ops.bn_scratch(C, DEV)
     y, mean, invstd = ops.bn_forward(x, gamma, beta, None, None, sums, 0.1, 1e-5, relu)
     ld = C + 24  # a column slice of a wider arena, with guard columns on both sides
-    arena = torch.zeros(2, R, ld, dtype=torch.float64, device=DEV)
+    arena = torch.zeros(2, R, ld, dtype=arena, device=DEV)
     S1, S2 = arena[0][:, 8:8 + C], arena[1][:, 8:8 + C]
     sums_b = ops.bn_scratch(C, DEV)
     dx, dgamma, dbeta = ops.bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, R, sums_b, relu, True)
@@ -140,11 +142,11 @@ def test_backward_matches_fp64_autograd_and_class_rows(native, shape, relu):
     o1, o2 = ref.outside_stats(v.cpu(), label, K)
     r1, r2 = torch.cat([r1, o1[None]]), torch.cat([r2, o2[None]])
     mass = torch.cat([ref.abs_mass(v.cpu(), label, K), ref.outside_stats(v.abs().cpu(), label, K)[0][None]])
-    e1 = (S1.cpu() - r1).abs()
+    e1 = (S1.double().cpu() - r1).abs()
     assert (e1 <= 1e-5 * mass + 1e-30).all(), "S1 rows: max rel-to-mass %.3g" % (e1 / (mass + 1e-30)).max()
-    e2 = (S2.cpu() - r2).abs()
+    e2 = (S2.double().cpu() - r2).abs()
     assert (e2 <= 1e-5 * r2 + 1e-30).all(), "S2 rows"
-    assert ((S1.sum(0) - dgamma.double()).abs().cpu() <= 1e-6 * mass_g.cpu() + 1e-30).all(), "row-sum identity: sum_k S1 == dgamma"
+    assert ((S1.double().sum(0) - dgamma.double()).abs().cpu() <= 2e-6 * mass_g.cpu() + 1e-30).all(), "row-sum identity: sum_k S1 == dgamma"
     # guard columns untouched
     assert float(arena[:, :, :8].abs().sum()) == 0.0 and float(arena[:, :, 8 + C:].abs().sum()) == 0.0
     # no input gradient wanted: same sums, no dx

@@ -122,9 +122,10 @@ def test_row_sums_are_the_gradient_autograd_hands_out(native):
     out = model(x, y.long(), deepsup=True)  # noqa
     (out["loss"] if isinstance(out, dict) else out).backward()
     sc.flush()
-    rows = sc.step_arena[0].sum(0).cpu().numpy()
+    both = sc.step_arena[0] + sc.step_arena32[0].double()  # hook-fed fp64 rows + the fused layers' fp32 rows
+    rows = both.sum(0).cpu().numpy()
     grads = torch.cat([m.weight.grad.reshape(-1) for _, m in sc.layers]).cpu().numpy()
-    mass = sc.step_arena[0].abs().sum(0).cpu().numpy()
+    mass = both.abs().sum(0).cpu().numpy()
     # fused layers: rows and gradient come out of ONE kernel (fp64 totals rounded once).  The few maps the fused path does
     # not take (1x1 pooled maps) keep torch's BN: there the gradient is cuDNN's own fp32 reduction (SURVEY app. C form)
     fused = np.concatenate([np.full(m.weight.numel(), "forward" in m.__dict__ and m.weight.numel() % 4 == 0) for _, m in sc.layers])
