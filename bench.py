@@ -432,7 +432,11 @@ def roofline_of(res, K, mb, nhwc):
             "class_stats_nhwc_kernel" if nhwc else "class_stats_kernel")
     tr = (traffic or {}).get("fused" if res["fused_on"] else "deferred")
     return {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+            "peak_source": peak_src,
+            # DRAM bytes per launch from the committed ncu --set full capture: where the capture covers a SUBSET of the step's
+            # launches (the per-layer launches of the fused path) its measured traffic / algorithmic ratio is applied to this
+            # run's average algorithmic bytes per launch, so that the two figures refer to the same launches
+            "traffic": (tr["ratio"] * res["dom_bytes"] / max(res["dom_launches"], 1) if "ratio" in tr else tr["dram_bytes_per_launch"]) if tr else None,
             "traffic_note": tr.get("note") if tr else "no ncu --set full capture recorded for this path yet",
             "launches": res["dom_launches"], "algorithmic_bytes_per_launch": res["dom_bytes"] / max(res["dom_launches"], 1),
             "avg_launch_ms": res["dom_ms"] / max(res["dom_launches"], 1), "share_of_step": res["share"],
