@@ -311,8 +311,9 @@ class Ctx:
         t = self.torch
         return [(x.to(self.dev).contiguous(memory_format=t.channels_last) if self.nhwc else x.to(self.dev), y.to(self.dev)) for x, y in host]
 
-    def timed(self, step_fn, first, n, nvtx=None):
-        """n steps bracketed by barrier + synchronize on both sides, CUDA events on the current stream, max over ranks."""
+    def timed(self, step_fn, first, n, nvtx=None, finish=None):
+        """n steps bracketed by barrier + synchronize on both sides, CUDA events on the current stream, max over ranks.
+        finish: called before the end event is recorded (joins side-stream work into the timed region)."""
         t = self.torch
         self.barrier()
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
@@ -323,6 +324,8 @@ class Ctx:
             step_fn(s)
             marks.append(t.cuda.Event(enable_timing=True))
             marks[-1].record()
+        if finish is not None:
+            finish()
         e1.record()
         if rng is not None:
             t.cuda.nvtx.range_end(rng)
@@ -377,7 +380,7 @@ def measure_run(ctx, model, c, resident, K, W, prime, gidx, timing_region=True, 
             tstep(s)
         t.cuda.synchronize()
         sc.reset_timing(drop_events=run._graph is None)
-        ms_t, ms_local, _ = ctx.timed(tstep, W, K)
+        ms_t, ms_local, _ = ctx.timed(tstep, W, K, finish=run.sync_scores)
         t.cuda.synchronize()
         d_ms, d_bytes, d_n, fused_on = dominant(sc)
         res.update(timing_ms=ms_t, phases=phase_table(sc, K, max(ms_local, 1e-9)), dom_ms=d_ms, dom_bytes=d_bytes, dom_launches=d_n,
@@ -402,7 +405,7 @@ def measure_run(ctx, model, c, resident, K, W, prime, gidx, timing_region=True, 
     replays0 = run.graph_replays
     mem0 = t.cuda.memory_stats(ctx.dev)
     t_wall0 = time.time()
-    ms, _, step_ms = ctx.timed(step, W, K, nvtx="timed")
+    ms, _, step_ms = ctx.timed(step, W, K, nvtx="timed", finish=run.sync_scores)
     t_wall1 = time.time()
     # kernels of this library inside the timed region: launched eagerly + (graph replays x kernels captured per replay)
     launches = ops.launch_count() - launches0 + (run.graph_replays - replays0) * run.graph_launches
@@ -518,6 +521,7 @@ def run_b200_arm(args, c):
                        graph=not args.no_graph)
     clocks = sampler.stop(*main["wall"]) if sampler else None
     sc = main["scorer"]
+    main["run"].sync_scores()
     value = K * mb * world / (main["ms"] * 1e-3)
     roofline = roofline_of(main, K, mb, ctx.nhwc)
     sc.all_reduce_totals()  # the single end-of-pass statistics all-reduce (outside the per-step timing, reported below)

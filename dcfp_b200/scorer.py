@@ -578,6 +578,9 @@ class CalibrationRun:
         self._graph_grads = []   # (parameter, its .grad tensor inside the graph's pool)
         self.graph_replays = 0
         self.graph_launches = 0
+        dist = torch.distributed
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self._comm_stream = torch.cuda.Stream(device=self.device) if (multi and mode == "bwd") else None
         self._open()
 
     def _open(self):
@@ -690,9 +693,25 @@ class CalibrationRun:
         else:
             dgamma, loss = dgamma.clone(), loss.clone()  # the graph's outputs are overwritten by the next replay
         if sc.mode == "bwd":
-            average_over_ranks(dgamma, self.group)
-            sc.eic_step(dgamma)
+            if self._comm_stream is None:
+                average_over_ranks(dgamma, self.group)
+                sc.eic_step(dgamma)
+            else:
+                # N > 1: the all-reduce of this step's dgamma and the EIC update it feeds run on a side stream -- the score
+                # state only has to be final when it is read, so the next step's forward does not wait for the slowest rank
+                # of this one (ranks may drift by up to a step instead of meeting at every all-reduce)
+                main = torch.cuda.current_stream(self.device)
+                self._comm_stream.wait_stream(main)
+                with torch.cuda.stream(self._comm_stream):
+                    average_over_ranks(dgamma, self.group)
+                    sc.eic_step(dgamma)
+                dgamma.record_stream(self._comm_stream)
         return loss
+
+    def sync_scores(self):
+        """Makes the current stream wait for the side-stream EIC updates (N > 1); call before reading `scorer.eic`."""
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
     def close(self, keep_graph=False):
         """Restores the model (hooks off, running statistics, train / eval mode, requires_grad).  keep_graph: the captured
@@ -701,6 +720,7 @@ class CalibrationRun:
             self._graph, self._graph_grads = None, []  # releases the graph's private memory pool
         if self.closed:
             return
+        self.sync_scores()
         self.closed = True
         for p_ in self._frozen:
             p_.requires_grad_(True)
@@ -837,6 +857,7 @@ def score_calibration_set(model, images, labels, num_classes, micro_batch=2, r=0
             consumed[b].record(main_stream)
             losses[step:step + 1].copy_(loss.reshape(1), non_blocking=True)
             d2h += 4
+        run.sync_scores()
         if return_class_stats:
             run.scorer.all_reduce_totals()
     finally:
