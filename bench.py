@@ -22,7 +22,7 @@ Printed JSON line (rank 0):
                copied host->device from pinned memory and the loss is read back; scorer set-up and the final score read-back
                are inside the timed region
   cpu_baseline the reference's CPU path on this box's host cores (bounded sample)
-  extras       (N = 1) scores_only, unfused (round-1 path: cuDNN BN + hook-fed deferred K1), producer_only (plain torch
+  extras       (N = 1) scores_only, bf16_autocast, unfused (round-1 path: cuDNN BN + hook-fed deferred K1), producer_only (plain torch
                fwd+bwd: what the path costs on top), conv_fp32, other_configs (c3, c4), sweep (calibration-set sizes)
 `--impl reference` times the reference's own CPU implementation: the UNMODIFIED reference modules from baseline/_ref
 (scripts/vendor_reference.py; kind "reference") when present, else the oracle port (kind "port").
@@ -585,6 +585,9 @@ def run_b200_arm(args, c):
         bare("producer_only")
         extras["producer_only"]["what"] = "plain torch fwd + bwd of the same net (cuDNN BN, no scorer): the feature-map producer alone"
         extras["producer_only"]["path_overhead_ms_per_step"] = main["ms"] / K - extras["producer_only"]["ms_per_step"]
+        short("bf16_autocast", graph=True, autocast_dtype=torch.bfloat16)
+        extras["bf16_autocast"]["what"] = ("forward under torch.autocast(bfloat16): bf16 convolutions and bf16 feature maps through the fused BN "
+                                           "kernels (fp32 statistics / sums); NOT the reference's fp32 arithmetic -- scores differ at bf16 level")
         ctx.set_conv_math(False)
         short("conv_fp32", Ks=3, Ws=2)
         extras["conv_fp32"]["what"] = "IEEE fp32 convolutions (cudnn.allow_tf32=False), channels_last, fused path"

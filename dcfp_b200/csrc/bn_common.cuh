@@ -16,8 +16,8 @@ constexpr int kBnStripes = 4;
 
 constexpr int kBnMaxCtas = 512;  // grid-barrier flags of the cooperative kernels (one per CTA; grids are <= #SMs)
 
-// scratch = double stripes[kBnStripes][2][C] | float coef[5][C] | unsigned counter, pad[3] | unsigned flags[kBnMaxCtas];
-// ZERO on entry
+// scratch = double stripes[kBnStripes][2][C] | float coef[5][C] (cooperative forward: scale, shift) | unsigned counter,
+// pad[3] | unsigned flags[kBnMaxCtas] (cooperative forward's grid barrier); ZERO on entry
 __host__ __device__ inline size_t bn_scratch_bytes(int C) {
   return static_cast<size_t>(kBnStripes) * 2 * C * sizeof(double) + static_cast<size_t>(5) * C * sizeof(float) + 16 +
          kBnMaxCtas * sizeof(unsigned);
@@ -44,31 +44,6 @@ struct BnFinal {
   float eps, momentum;
   int C;
 };
-
-// true in exactly one CTA per launch: the one that arrives last.  Must be called by ALL threads of every CTA after
-// their global atomics; resets the counter for the next launch that reuses the scratch.
-__device__ __forceinline__ bool bn_last_cta(unsigned* counter) {
-  __shared__ unsigned s_ticket;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
-  __syncthreads();
-  const bool last = s_ticket == gridDim.x * gridDim.y - 1;
-  if (last) {
-    __threadfence();
-    if (threadIdx.x == 0) *counter = 0u;
-  }
-  return last;
-}
-
-__device__ __forceinline__ void bn_sum_stripes(const double* stripes, int C, int c, double& s0, double& s1) {
-  s0 = s1 = 0.0;
-#pragma unroll
-  for (int s = 0; s < kBnStripes; ++s) {
-    s0 += __ldcg(stripes + static_cast<size_t>(s) * 2 * C + c);
-    s1 += __ldcg(stripes + static_cast<size_t>(s) * 2 * C + C + c);
-  }
-}
 
 // stripe sums of 4 consecutive channels (c0 % 4 == 0): 128-bit read-only loads through L1 -- the stripes were written by the
 // PREVIOUS kernel on the stream, and the blocks of an SM all read the same few KB
@@ -120,79 +95,6 @@ __device__ __forceinline__ void bn_coef_backward4(const BnFinal& F, int c0, floa
     d_f[j] = static_cast<float>(a * (static_cast<double>(mm[j]) * ii[j] * mg - mb));
     zs[j] = __fmul_rn(gg[j], ii[j]);
     zt[j] = __fmaf_rn(-mm[j], zs[j], bb[j]);
-  }
-}
-
-// single-channel forms
-__device__ __forceinline__ void bn_coef_forward(const BnFinal& F, int c, float& mean_f, float& invstd_f, float& scale, float& shift,
-                                                double& mean, double& var) {
-  double s, q;
-  bn_sum_stripes(bn_stripes(F.scratch), F.C, c, s, q);
-  mean = s * F.inv_m;
-  var = fmax(q * F.inv_m - mean * mean, 0.0);
-  mean_f = static_cast<float>(mean);
-  invstd_f = static_cast<float>(rsqrt(var + static_cast<double>(F.eps)));
-  // the SAME two fp32 expressions are re-evaluated by the backward kernels from the saved mean / invstd: bit-exact ReLU gate
-  scale = __fmul_rn(F.gamma[c], invstd_f);
-  shift = __fmaf_rn(-mean_f, scale, F.beta[c]);
-}
-// backward: stripes hold (sum dz, sum dz * xhat);  dx = a * dz + b * x + d,  gate z = fma(x, zs, zt)
-__device__ __forceinline__ void bn_coef_backward(const BnFinal& F, int c, float& a_f, float& b_f, float& d_f, float& zs, float& zt,
-                                                 double& dgamma, double& dbeta) {
-  bn_sum_stripes(bn_stripes(F.scratch), F.C, c, dbeta, dgamma);
-  const float mean_f = F.mean[c], invstd_f = F.invstd[c], g = F.gamma[c];
-  const double a = static_cast<double>(g) * invstd_f;
-  const double mg = dgamma * F.inv_m, mb = dbeta * F.inv_m;
-  a_f = static_cast<float>(a);
-  b_f = static_cast<float>(-a * invstd_f * mg);
-  d_f = static_cast<float>(a * (static_cast<double>(mean_f) * invstd_f * mg - mb));
-  zs = __fmul_rn(g, invstd_f);
-  zt = __fmaf_rn(-mean_f, zs, F.beta[c]);
-}
-
-// (cooperative forward / tests) forward: stripes hold (sum x, sum x^2).  coef[0] = scale = gamma * invstd, coef[1] = shift = fma(-mean, scale, beta):
-// the backward re-evaluates these two fp32 expressions from the saved mean / invstd, so the ReLU gate is bit-exact.
-__device__ __forceinline__ void bn_finalize_forward(const BnFinal& F) {
-  float* coef = bn_coef(F.scratch, F.C);
-  const double* stripes = bn_stripes(F.scratch);
-  for (int c = threadIdx.x; c < F.C; c += blockDim.x) {
-    double s, q;
-    bn_sum_stripes(stripes, F.C, c, s, q);
-    const double mean = s * F.inv_m;
-    const double var = fmax(q * F.inv_m - mean * mean, 0.0);
-    const float mean_f = static_cast<float>(mean);
-    const float invstd_f = static_cast<float>(rsqrt(var + static_cast<double>(F.eps)));
-    const float scale = __fmul_rn(F.gamma[c], invstd_f);
-    coef[c] = scale;
-    coef[F.C + c] = __fmaf_rn(-mean_f, scale, F.beta[c]);
-    F.mean[c] = mean_f;
-    F.invstd[c] = invstd_f;
-    if (F.running_mean != nullptr) {
-      F.running_mean[c] = static_cast<float>((1.0 - F.momentum) * F.running_mean[c] + F.momentum * mean);
-      F.running_var[c] = static_cast<float>((1.0 - F.momentum) * F.running_var[c] + F.momentum * var * F.unbias);
-    }
-  }
-}
-
-// backward: stripes hold (sum dz, sum dz * xhat).  dx = a * dz + b * x + d with a = gamma * invstd,
-// b = -a * invstd * dgamma / M, d = a * (mean * invstd * dgamma / M - dbeta / M);  coef = [a, b, d, zscale, zshift].
-__device__ __forceinline__ void bn_finalize_backward(const BnFinal& F) {
-  float* coef = bn_coef(F.scratch, F.C);
-  const double* stripes = bn_stripes(F.scratch);
-  for (int c = threadIdx.x; c < F.C; c += blockDim.x) {
-    double dbeta, dgamma;
-    bn_sum_stripes(stripes, F.C, c, dbeta, dgamma);
-    const float mean_f = F.mean[c], invstd_f = F.invstd[c], g = F.gamma[c];
-    const double a = static_cast<double>(g) * invstd_f;
-    const double mg = dgamma * F.inv_m, mb = dbeta * F.inv_m;
-    coef[c] = static_cast<float>(a);
-    coef[F.C + c] = static_cast<float>(-a * invstd_f * mg);
-    coef[2 * F.C + c] = static_cast<float>(a * (static_cast<double>(mean_f) * invstd_f * mg - mb));
-    const float zs = __fmul_rn(g, invstd_f);
-    coef[3 * F.C + c] = zs;
-    coef[4 * F.C + c] = __fmaf_rn(-mean_f, zs, F.beta[c]);
-    F.dgamma[c] = static_cast<float>(dgamma);
-    F.dbeta[c] = static_cast<float>(dbeta);
   }
 }
 

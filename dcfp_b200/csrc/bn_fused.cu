@@ -75,7 +75,6 @@ struct BnArgs {
   const void* x;
   void* y;           // forward: y;  backward: dx
   const void* dy;    // backward
-  const float* coef; // [5][C] left by the reduction pass: forward (scale, shift); backward (a, b, d, zscale, zshift)
   long long M;       // pixels: N * h * w
   int C;
   int rows_per_block;
@@ -97,7 +96,7 @@ struct BnThread {
   }
 };
 
-// F1: per-channel sum x, sum x^2 -> scratch stripes; the last block finalises (bn_finalize_forward).
+// F1: per-channel sum x, sum x^2 -> scratch stripes (bn_apply_kernel turns them into scale / shift in its prologue).
 // 2-D grid: blockIdx.y owns a slab of 32 * kCh channels, blockIdx.x a contiguous range of rows -- fp64 atomics are scarce
 // (a launch that sent 2 * C of them from each of 592 blocks spent 15-50 us on them), so what matters is the number of ROW
 // blocks: (592 / column blocks) * 2 * C atomics per launch, ~150 k for every layer shape.
@@ -320,7 +319,6 @@ BnArgs plan_rows(const BnArgs& A0, int per_sm, dim3* grid) {
 BnArgs stream_args(const dcfp_bn_desc* d) {
   BnArgs A{};
   A.x = d->x;
-  A.coef = bn_coef(d->scratch, d->C);
   A.M = static_cast<long long>(d->N) * d->h * d->w;
   A.C = d->C;
   return A;

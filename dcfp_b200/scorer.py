@@ -553,12 +553,15 @@ class CalibrationRun:
     all-reduce before the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
 
     def __init__(self, model, num_classes, r=0.999, mode="bwd", restore_bn_stats=True, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, process_group=None, seed=None, scores_only=False, fused=True, graph=True):
+                 timing=False, process_group=None, seed=None, scores_only=False, fused=True, graph=True, autocast_dtype=None):
         ops.require_gpu()
         self.model = model
         self.seed = seed
         self.scores_only = bool(scores_only)
         self.restore_bn_stats = bool(restore_bn_stats)
+        # autocast_dtype=torch.bfloat16: the forward runs under torch.autocast -- bf16 convolutions and bf16 feature maps, which
+        # the fused BN kernels / K1 read and write as bf16 (fp32 statistics and sums).  Not the reference's arithmetic (fp32).
+        self.autocast_dtype = autocast_dtype
         self._frozen = []
         self.device = next(model.parameters()).device
         # restore_bn_stats puts num_batches_tracked back at close(): the fused layers then skip its per-layer increment
@@ -631,11 +634,15 @@ class CalibrationRun:
         sc = self.scorer
         sc.set_labels(y)
         self.model.zero_grad(set_to_none=True)
-        out = self.model(x, y if y.dtype == torch.long else y.long(), deepsup=True)
+        if self.autocast_dtype is not None:
+            with torch.autocast(device_type="cuda", dtype=self.autocast_dtype):
+                out = self.model(x, y if y.dtype == torch.long else y.long(), deepsup=True)
+        else:
+            out = self.model(x, y if y.dtype == torch.long else y.long(), deepsup=True)
         loss = out["loss"] if isinstance(out, dict) else out
         if sc.mode == "bwd":
             loss.backward()
-        return sc.fold_step(), loss.detach()
+        return sc.fold_step(), loss.detach().float()
 
     def _capture(self, key, x, y):
         gx, gy = x.clone(memory_format=torch.preserve_format), y.clone()
