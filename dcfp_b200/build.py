@@ -21,6 +21,8 @@ OPS_LIB = os.path.join(LIBDIR, "dcfp_torch_ops.so")
 CU_SOURCES = ["class_stats.cu", "bn_fused.cu", "eic_select.cu", "gather.cu", "balance.cu", "abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-extended-lambda",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
+if os.environ.get("DCFP_K1_TRACE") == "1":  # development build: per-phase timestamps inside the fused K1 kernel (scripts/k1_trace.py)
+    NVCC_FLAGS.append("-DDCFP_K1_TRACE")
 
 
 def _nvcc():

@@ -282,3 +282,9 @@ extern "C" int dcfp_label_keys(const void* label, int label_dtype, int N, int H0
       static_cast<float>(W0) / static_cast<float>(w), keys, cnt);
   return finish_launch("label_keys");
 }
+
+#ifdef DCFP_K1_TRACE
+extern "C" int dcfp_debug_k1_trace(unsigned long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, dcfp::g_k1_trace, sizeof(unsigned long long) * 160 * 8));
+}
+#endif

@@ -102,6 +102,21 @@ struct BoxRow<__nv_bfloat16> {
 
 constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-boxes, or 2 (x, dy) pairs
 
+// -DDCFP_K1_TRACE (DCFP_K1_TRACE=1 python -m dcfp_b200.build): thread 0 of every CTA of the fused instantiation stamps
+// %globaltimer at seven points of the kernel (scripts/k1_trace.py prints the per-phase times: this is how the merge tree
+// and the prologue were found to be 30 % + 12 % of a 17 MB launch).  Compiled out otherwise.
+#ifdef DCFP_K1_TRACE
+__device__ unsigned long long g_k1_trace[160 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define K1_TRACE(i) do { if (FUSED && threadIdx.x == 0) g_k1_trace[blockIdx.x * 8 + (i)] = gtime(); } while (0)
+#else
+#define K1_TRACE(i) do { } while (0)
+#endif
+
 template <typename T, bool BWD, bool AFFINE, int MAXL, int FUSED = 0>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P, const NhwcFused F) {
@@ -118,6 +133,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   float* slots = reinterpret_cast<float*>(smem + kNhwcWarps * kStages * kStageBytes);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(slots + kNhwcWarps * kNhwcSlots * 256);
 
+  K1_TRACE(0);
   const unsigned K = static_cast<unsigned>(P.K);
   const int n_tiles = P.tile_prefix[P.n_layers];
   const int t_first = static_cast<int>(static_cast<long long>(blockIdx.x) * n_tiles / gridDim.x);
@@ -154,8 +170,9 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   int last_slot = 0;
   const uint32_t mine_u32 = smem_u32(mine);
 
-  auto row_to_arena = [&](int slot, unsigned cls) {  // fp32 row -> fp64 arena, row zeroed
-    float4 a = mine[slot * 64], b = mine[slot * 64 + 32];
+  // one class row (the lane's 4 channels: S1 in a, S2 in b) -> arena.  fp32 vector reductions into the per-step fp32 arena
+  // of the fused BN backward, fp64 scalar atomics otherwise.  Called by all lanes of a warp.
+  auto emit_row = [&](unsigned cls, float4 a, float4 b) {
     if (fold2) {  // lanes 16-31 hold the same 64 channels (odd pixels): one atomic per channel, not two
       a.x += __shfl_xor_sync(0xffffffffu, a.x, 16);
       a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
@@ -166,26 +183,28 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       b.z += __shfl_xor_sync(0xffffffffu, b.z, 16);
       b.w += __shfl_xor_sync(0xffffffffu, b.w, 16);
     }
+    if (!lane_on || (fold2 && lane >= 16) || P.debug_skip_rows) return;
     if (FUSED && F.S1f != nullptr) {
-      if (lane_on && !(fold2 && lane >= 16) && !P.debug_skip_rows) {
-        const size_t o = cls * ld + static_cast<size_t>(c0);
-        if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)
-          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(F.S1f + o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-        if (b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f)
-          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(F.S2f + o), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
-      }
-    } else if (lane_on && !(fold2 && lane >= 16) && !P.debug_skip_rows) {
-      double* d1 = out1 + cls * ld;
-      double* d2 = out2 + cls * ld;
-      if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));
-      if (a.y != 0.f) atomicAdd(d1 + 1, static_cast<double>(a.y));
-      if (a.z != 0.f) atomicAdd(d1 + 2, static_cast<double>(a.z));
-      if (a.w != 0.f) atomicAdd(d1 + 3, static_cast<double>(a.w));
-      if (b.x != 0.f) atomicAdd(d2 + 0, static_cast<double>(b.x));
-      if (b.y != 0.f) atomicAdd(d2 + 1, static_cast<double>(b.y));
-      if (b.z != 0.f) atomicAdd(d2 + 2, static_cast<double>(b.z));
-      if (b.w != 0.f) atomicAdd(d2 + 3, static_cast<double>(b.w));
+      const size_t o = cls * ld + static_cast<size_t>(c0);
+      if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)
+        asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(F.S1f + o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+      if (b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f)
+        asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(F.S2f + o), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+      return;
     }
+    double* d1 = out1 + cls * ld;
+    double* d2 = out2 + cls * ld;
+    if (a.x != 0.f) atomicAdd(d1 + 0, static_cast<double>(a.x));
+    if (a.y != 0.f) atomicAdd(d1 + 1, static_cast<double>(a.y));
+    if (a.z != 0.f) atomicAdd(d1 + 2, static_cast<double>(a.z));
+    if (a.w != 0.f) atomicAdd(d1 + 3, static_cast<double>(a.w));
+    if (b.x != 0.f) atomicAdd(d2 + 0, static_cast<double>(b.x));
+    if (b.y != 0.f) atomicAdd(d2 + 1, static_cast<double>(b.y));
+    if (b.z != 0.f) atomicAdd(d2 + 2, static_cast<double>(b.z));
+    if (b.w != 0.f) atomicAdd(d2 + 3, static_cast<double>(b.w));
+  };
+  auto row_to_arena = [&](int slot, unsigned cls) {  // the warp's own row -> arena, row zeroed
+    emit_row(cls, mine[slot * 64], mine[slot * 64 + 32]);
     mine[slot * 64] = make_float4(0.f, 0.f, 0.f, 0.f);
     mine[slot * 64 + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
   };
@@ -253,53 +272,68 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       b = fma2(b, sc23, sf23);
     }
   };
-  // End of a (layer, slab group): rows -> arena.  The warps of a CTA that share a slab (phases > 1) first merge their
-  // rows pairwise into the lowest one (tree over the phases, through shared memory), so the arena sees ONE atomic per
-  // (class, channel) and CTA instead of one per warp: same-address fp64 atomics serialise at ~38 cycles each in L2, which
-  // a per-layer launch (fused BN) pays in full at its tail.  Every warp of the CTA reaches fold() at the same tile
-  // boundaries, so the CTA barriers below are uniform.  Publishing area: the warp's own staging buffer (idle here).
-  auto fold = [&]() {
+  // End of a (layer, slab group): rows -> arena.  The warps of a CTA that share a slab (phases > 1) combine their rows
+  // first, so the arena sees ONE reduction per (class, channel) and CTA instead of one per warp (same-address atomics
+  // serialise in the L2 slice; a per-layer launch pays them in full at its tail).  ONE round: every warp publishes the
+  // class tags of its 12 rows, and after a single CTA barrier warp `phase` owns the classes c = phase (mod phases): it finds
+  // them among the <= 96 published tags with three ballots per class, sums those rows straight out of the other warps'
+  // slot memory and sends the result to the arena -- all warps emit in parallel.  (A pairwise tree over the phases -- three
+  // rounds of barrier + row_add + re-zero -- was 30 % of a 17 MB launch: scripts/k1_trace.py.)  Every warp of the CTA
+  // reaches fold() at the same tile boundaries, so the barriers are uniform.  Publishing area: the warp's own staging
+  // buffer (idle here).  last: no tile follows -- the rows need not be zeroed again.
+  auto fold = [&](bool last) {
+    K1_TRACE(3);
     if (phases > 1) {
       const int spc_ = kNhwcWarps / phases;
       auto pub = [&](int w) { return reinterpret_cast<unsigned*>(smem + static_cast<size_t>(w) * kStages * kStageBytes); };
-      for (int step = 1; step < phases; step <<= 1) {
-        if ((phase & (2 * step - 1)) == step) {  // donor of this round
-          if (!direct && lane < kNhwcSlots) pub(warp)[lane] = my_tag;
-          if (FUSED) {
-            f2* t = reinterpret_cast<f2*>(pub(warp) + 32) + lane * 4;
-            t[0] = tb01, t[1] = tb23, t[2] = tg01, t[3] = tg23;
+      if (lane < kNhwcSlots) pub(warp)[lane] = direct ? (static_cast<unsigned>(lane) < K ? static_cast<unsigned>(lane) : kFree) : my_tag;
+      if (FUSED) {
+        f2* t = reinterpret_cast<f2*>(pub(warp) + 32) + lane * 4;
+        t[0] = tb01, t[1] = tb23, t[2] = tg01, t[3] = tg23;
+      }
+      __syncthreads();
+      const int base_w = warp % spc_;
+      unsigned tg[3];  // position p = member * 12 + slot of the group's published tags; lane holds p = lane, lane + 32, lane + 64
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int p = lane + 32 * j;
+        tg[j] = p < phases * kNhwcSlots ? pub(base_w + (p / kNhwcSlots) * spc_)[p % kNhwcSlots] : kFree;
+      }
+      for (unsigned c = static_cast<unsigned>(phase); c < K; c += static_cast<unsigned>(phases)) {
+        unsigned m[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m[j] = __ballot_sync(0xffffffffu, tg[j] == c);
+        if ((m[0] | m[1] | m[2]) == 0u) continue;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          unsigned mask = m[j];
+          while (mask) {
+            const int p = __ffs(mask) - 1 + 32 * j;
+            mask &= mask - 1;
+            const float4* row = reinterpret_cast<const float4*>(slots + static_cast<size_t>(base_w + (p / kNhwcSlots) * spc_) * kNhwcSlots * 256) +
+                                (p % kNhwcSlots) * 64 + lane;
+            const float4 u = row[0], v = row[32];
+            a.x += u.x, a.y += u.y, a.z += u.z, a.w += u.w;
+            b.x += v.x, b.y += v.y, b.z += v.z, b.w += v.w;
           }
         }
-        __syncthreads();
-        if ((phase & (2 * step - 1)) == 0 && phase + step < phases) {  // receiver: merge the donor's rows into mine
-          const int d = warp + step * spc_;
-          const float4* drow = reinterpret_cast<const float4*>(slots + static_cast<size_t>(d) * kNhwcSlots * 256) + lane;
-          const int n_rows = direct ? static_cast<int>(K) : kNhwcSlots;
-          for (int i = 0; i < n_rows; ++i) {
-            const unsigned cls = direct ? static_cast<unsigned>(i) : pub(d)[i];
-            if (cls == kFree) continue;
-            const float4 a = drow[i * 64], b = drow[i * 64 + 32];
-            row_add(cls, pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
-          }
-          if (FUSED) {
-            const f2* t = reinterpret_cast<const f2*>(pub(d) + 32) + lane * 4;
+        emit_row(c, a, b);
+      }
+      if (FUSED) {  // the totals of the group: its first warp sums them
+        if (phase == 0) {
+          for (int mbr = 1; mbr < phases; ++mbr) {
+            const f2* t = reinterpret_cast<const f2*>(pub(base_w + mbr * spc_) + 32) + lane * 4;
             tb01 = add2(tb01, t[0]);
             tb23 = add2(tb23, t[1]);
             tg01 = add2(tg01, t[2]);
             tg23 = add2(tg23, t[3]);
           }
-        }
-        __syncthreads();
-        if ((phase & (2 * step - 1)) == step) {  // the donor's sums now live in the receiver
-          for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-          my_tag = kFree;
-          victim = 0;
-          used = 0;
-          last_key = 0xffffffffu;
+        } else {
           tb01 = tb23 = tg01 = tg23 = 0;
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes above, TMA writes next
+      K1_TRACE(4);
     }
     if (FUSED) {
       if (fold2) {
@@ -322,18 +356,24 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       }
       tb01 = tb23 = tg01 = tg23 = 0;
     }
-    if (direct) {
+    K1_TRACE(5);
+    if (phases > 1) {
+      if (last) return;
+      __syncthreads();  // the other warps of the group have read my rows
+      for (int i = 0; i < kNhwcSlots * 2; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes to the staging buffer, TMA writes next
+    } else if (direct) {
       for (unsigned k = 0; k < K; ++k) row_to_arena(static_cast<int>(k), k);
     } else {
       for (int slot = 0; slot < kNhwcSlots; ++slot) {
         const unsigned cls = __shfl_sync(0xffffffffu, my_tag, slot);
         if (cls != kFree) row_to_arena(slot, cls);
       }
-      my_tag = kFree;
-      victim = 0;
-      used = 0;
-      last_key = 0xffffffffu;
     }
+    my_tag = kFree;
+    victim = 0;
+    used = 0;
+    last_key = 0xffffffffu;
   };
 
   for (int tile = t_first; tile < t_last; ++tile) {
@@ -343,8 +383,9 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     const int t = tile - P.tile_prefix[layer];
     const int sg = t / L.n_chunks;
     const int chunk = t - sg * L.n_chunks;
-    if (layer != cur_layer || sg != cur_sg) {
-      if (cur_layer >= 0) fold();
+    const bool new_slab = layer != cur_layer || sg != cur_sg;
+    if (new_slab) {
+      if (cur_layer >= 0) fold(false);
       cur_layer = layer;
       cur_sg = sg;
       const int spc = L.spc;
@@ -358,33 +399,6 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       ld = static_cast<size_t>(L.ld);
       out1 = L.S1 + c0;
       out2 = L.S2 + c0;
-      sc01 = sc23 = pack2(1.f, 1.f);
-      sf01 = sf23 = 0;
-      if (lane_on && (BWD || AFFINE)) {
-        float sc[4], sf[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sc[j] = L.scale ? L.scale[c0 + j] : 1.f;
-          sf[j] = L.shift ? L.shift[c0 + j] : 0.f;
-          if (L.centered) sf[j] = -sf[j] * sc[j];
-        }
-        sc01 = pack2(sc[0], sc[1]);
-        sc23 = pack2(sc[2], sc[3]);
-        sf01 = pack2(sf[0], sf[1]);
-        sf23 = pack2(sf[2], sf[3]);
-      }
-      if (FUSED == 2 && lane_on) {  // needs scale = invstd, shift = mean (DCFP_AFFINE_INVSTD_MEAN)
-        float zs[4], zt[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          zs[j] = __fmul_rn(F.gamma[c0 + j], L.scale[c0 + j]);
-          zt[j] = __fmaf_rn(-L.shift[c0 + j], zs[j], F.beta[c0 + j]);
-        }
-        zs01 = pack2(zs[0], zs[1]);
-        zs23 = pack2(zs[2], zs[3]);
-        zt01 = pack2(zt[0], zt[1]);
-        zt23 = pack2(zt[2], zt[3]);
-      }
     }
 
     const int p_begin = chunk * L.px_per_chunk;
@@ -445,7 +459,38 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     fetch_keys(0, kcur);
     fetch_keys(32, knxt);
 
+    K1_TRACE(1);
     for (int s = 0; s < kStages; ++s) issue();
+    if (new_slab) {  // per-channel coefficients of the slab: loaded AFTER the first boxes are in flight (their global-load
+                     // latency used to sit in front of the first TMA issue: ~1 us of a 17 us launch)
+      sc01 = sc23 = pack2(1.f, 1.f);
+      sf01 = sf23 = 0;
+      if (lane_on && (BWD || AFFINE)) {
+        float sc[4], sf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc[j] = L.scale ? L.scale[c0 + j] : 1.f;
+          sf[j] = L.shift ? L.shift[c0 + j] : 0.f;
+          if (L.centered) sf[j] = -sf[j] * sc[j];
+        }
+        sc01 = pack2(sc[0], sc[1]);
+        sc23 = pack2(sc[2], sc[3]);
+        sf01 = pack2(sf[0], sf[1]);
+        sf23 = pack2(sf[2], sf[3]);
+      }
+      if (FUSED == 2 && lane_on) {  // needs scale = invstd, shift = mean (DCFP_AFFINE_INVSTD_MEAN)
+        float zs[4], zt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          zs[j] = __fmul_rn(F.gamma[c0 + j], L.scale[c0 + j]);
+          zt[j] = __fmaf_rn(-L.shift[c0 + j], zs[j], F.beta[c0 + j]);
+        }
+        zs01 = pack2(zs[0], zs[1]);
+        zs23 = pack2(zs[2], zs[3]);
+        zt01 = pack2(zt[0], zt[1]);
+        zt23 = pack2(zt[2], zt[3]);
+      }
+    }
     int stage = 0;
     for (int it = 0; it < n_my; ++it) {
       const int j = it & 31;
@@ -459,6 +504,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
         if (q < Q * kf) kw[q] = __shfl_sync(0xffffffffu, kcur[q], j);
       mbar_wait(my_bars + stage * 8, (parity_bits >> stage) & 1u);
       parity_bits ^= 1u << stage;
+      if (it == 0) K1_TRACE(2);
       const uint32_t box_lane = my_bufs + stage * kStageBytes + lane_off;
       if (fold2) {
         // pixel-pair rows: row r = pixels 2r (lanes 0-15) and 2r+1 (lanes 16-31); 8 rows = 16 key bytes = 4 words
@@ -568,7 +614,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       if (++stage == kStages) stage = 0;
     }
   }
-  if (cur_layer >= 0) fold();
+  if (cur_layer >= 0) fold(true);
+  K1_TRACE(6);
 }
 
 // NHWC: [rows = N*HW][cols = C], box = [G px][128 channels], no swizzle (a pixel row is read with one LDS per lane)
