@@ -117,7 +117,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define K1_TRACE(i) do { } while (0)
 #endif
 
-template <typename T, bool BWD, bool AFFINE, int MAXL, int FUSED = 0>
+// FOLD2: -1 = per layer at run time (grouped launches); 0 / 1 = known at compile time (the per-layer launches of the fused BN
+// backward: half of the accumulation code disappears -- the kernel is ~6 000 SASS instructions, and a launch that runs for
+// 12 us starts with a cold instruction cache every time)
+template <typename T, bool BWD, bool AFFINE, int MAXL, int FUSED = 0, int FOLD2 = -1>
 __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
     class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P, const NhwcFused F) {
   static_assert(FUSED == 0 || BWD, "the fused BN-backward functor reads x and dy");
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
 
   int layer = 0, cur_layer = -1, cur_sg = -1;
   int phases = kNhwcWarps, phase = 0, c0 = 0, col0 = 0;
-  bool lane_on = false, fold2 = false;
+  bool lane_on = false, fold2 = FOLD2 > 0;
   double* out1 = nullptr;  // &S1[c0], &S2[c0] of the current layer
   double* out2 = nullptr;
   size_t ld = 0;
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       col0 = (sg * spc + warp % spc) * kNhwcSlab;
       c0 = col0 + lane * 4;
       lane_on = c0 < L.C;  // C % 4 == 0: a lane's 4 channels are all inside or all outside (TMA zero-fills outside)
-      fold2 = L.fold2 != 0;
+      fold2 = FOLD2 < 0 ? (L.fold2 != 0) : (FOLD2 > 0);
       if (fold2) c0 &= 63;  // columns 64..127 of a pixel-pair row are channels 0..63 of the odd pixel
       ld = static_cast<size_t>(L.ld);
       out1 = L.S1 + c0;
@@ -755,6 +758,8 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPl
                       1024 /* base alignment slack */;
   void (*kern)(NhwcParams<MAXL, kTens>, NhwcFused) = class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED>;
   if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL, 0>;
+  if (FUSED) kern = P.L[0].fold2 ? class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED, (FUSED ? 1 : -1)>
+                                 : class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED, (FUSED ? 0 : -1)>;
   NhwcFused F{};
   if (FUSED) {
     DCFP_REQUIRE(fused != nullptr && n == 1 && fused->fin.scratch != nullptr, DCFP_EINVAL, "class_stats: fused BN backward needs one layer");
