@@ -536,7 +536,7 @@ def run_b200_arm(args, c):
         allreduce_ms = ctx.max_over_ranks(ea.elapsed_time(eb))
     arena_bytes = sc.total_arena.numel() * 8
     sum_c = sc.total_channels
-    fused_layers = sc.fused_layer_calls
+    fused_layers, fused_tails = sc.fused_layer_calls, sc.fused_tail_calls
     main["run"].close()
     extras = {}
 
@@ -566,6 +566,9 @@ def run_b200_arm(args, c):
         # (2) what the path costs on top of the bare producer, and the alternatives
         short("scores_only", scores_only=True, graph=True)
         extras["scores_only"]["what"] = "non-BN parameters frozen: no weight-gradient convolutions; same scores (tests/test_gpu_scorer.py)"
+        short("no_residual_fusion", graph=True, fuse_residual=False)
+        extras["no_residual_fusion"]["what"] = ("fused BN(+ReLU) kernels, but bn3 -> (+ shortcut) -> ReLU of every bottleneck left as BN kernel + "
+                                                "torch add + torch ReLU (the round-2 path before the fused tail)")
         short("unfused", fused=False, timing_region=True, graph=True)
         extras["unfused"]["what"] = "round-1 path: torch/cuDNN BatchNorm + ReLU, hook-fed K1 deferred into grouped launches"
 
@@ -681,12 +684,12 @@ def run_b200_arm(args, c):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": main["ms"] / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": shared_config(c, args),
-                "arm": {"images_timed": K * mb * world, "sum_scored_channels": sum_c, "fused_bn_layer_calls_total": fused_layers,
+                "arm": {"images_timed": K * mb * world, "sum_scored_channels": sum_c, "fused_bn_layer_calls_total": fused_layers, "fused_bn_residual_tail_calls_total": fused_tails,
                         "labels_mean_class_run_px_at_stride8": run_len, "labels_classes_per_image": n_cls,
                         "conv_math": ("tf32 (torch default cudnn.allow_tf32=True, as the reference's train.py runs its convolutions)"
                                       if tf32 else "fp32 (cudnn.allow_tf32=False)") + "; the path's own arithmetic is fp32 (fp64 across CTAs)",
-                        "bn": ("fused: dcfp BN(+ReLU) forward (one cooperative launch) / backward kernels, class-keyed sums inside the BN "
-                               "backward") if fused_on else "torch/cuDNN BatchNorm + ReLU, hook-fed deferred K1",
+                        "bn": ("fused: dcfp BN(+ReLU) forward (statistics + normalise launches; bn3 + shortcut + ReLU of a bottleneck in "
+                               "the same normalise pass) / backward kernels, class-keyed sums inside the BN backward") if fused_on else "torch/cuDNN BatchNorm + ReLU, hook-fed deferred K1",
                         "l2": "per-step feature maps (%.1f GB read by the dominant kernel) exceed the 126 MB L2; no explicit flush" % (
                             roofline["algorithmic_bytes_per_image"] * mb / 1e9),
                         "layout": args.layout, "backward": "scores_only (no weight-gradient convolutions)" if args.scores_only else

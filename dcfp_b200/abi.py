@@ -31,7 +31,7 @@ class BnDesc(ctypes.Structure):
                                                "scratch", "keys", "S1", "S2", "dgamma", "dbeta")] + \
                [(n, ctypes.c_int32) for n in ("N", "C", "h", "w", "dtype", "relu", "K", "ld")] + \
                [("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("phases", ctypes.c_int32), ("arena_f32", ctypes.c_int32),
-                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64)]
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64), ("residual", ctypes.c_void_p)]
 
 
 class GatherDesc(ctypes.Structure):

@@ -1,5 +1,5 @@
 // Fused BN: scratch layout shared by the reduction kernels (bn_stats_kernel, the FUSED instantiation of K1) and the
-// element-wise kernels (bn_apply_kernel, bn_dx_kernel), and the "last CTA finalises" step between them.
+// element-wise kernels (bn_apply_kernel, bn_dx_kernel), and the per-channel coefficient math between them.
 //
 // Same-address fp64 atomics serialise in the L2 slice at ~38 cycles each (measured: a per-layer K1 launch whose 1 184
 // warps each added their rows to the same 2*C addresses spent 20-60 us in that tail).  So per-channel totals go to one of

@@ -4,15 +4,16 @@
 // networks/tools/aspp.py:15-24) and, in loss.backward() (train.py:265), autograd's ReLU + BN backward whose
 // bn.weight.grad pruners/dcfp_pruner.py:18 reads.  Every pass below is HBM/L2-bound streaming over channels_last maps:
 //
-//   forward   F1  bn_stats_kernel: sum x, sum x^2 per channel (fp32 per thread, fp64 across blocks, striped atomics); the
-//                 last block turns them into mean / invstd / running statistics and the fp32 (scale, shift) pair
-//             F2  bn_apply_kernel: y = max(fma(x, scale, shift), 0), walking the rows backwards (what F1 read last is
-//                 what the L2 still holds)
+//   forward   F1  bn_stats_kernel: sum x, sum x^2 per channel (fp32 per thread, fp64 across blocks, striped atomics)
+//             F2  bn_apply_kernel: every block sums the stripes of its channels into (scale, shift) in its prologue
+//                 (block row 0 also writes mean / invstd / running statistics), then y = max(fma(x, scale, shift), 0),
+//                 walking the rows backwards (what F1 read last is what the L2 still holds)
 //   backward  B1  K1 with the fused functor: gate recomputed from the SAME fma(x, scale, shift) the forward evaluated,
 //                 dz = gate ? dy : 0, v = dz * xhat;  class rows S1[k][c] += v, S2[k][c] += v^2 (the scorer's arena)
 //                 and the totals sum dz (dbeta), sum v (dgamma) -- ONE read of (x, dy) yields the reference's score
-//                 input, the class-conditional statistics and what dx needs; the last CTA leaves the dx coefficients
-//             B2  bn_dx_kernel: dx = a * dz + b * x + d, re-reading (x, dy) -- from L2 when the layer fits (B1 loads with
+//                 input, the class-conditional statistics and what dx needs
+//             B2  bn_dx_kernel: prologue sums the stripes into (a, b, d) (block row 0 writes dgamma / dbeta), then
+//                 dx = a * dz + b * x + d, re-reading (x, dy) -- from L2 when the layer fits (B1 loads with
 //                 normal L2 priority, B2 walks the rows in reverse order)
 //
 // No dense contraction anywhere: no tensor cores.  fp32 inside a thread / warp, fp64 across CTAs.
@@ -75,6 +76,7 @@ struct BnArgs {
   const void* x;
   void* y;           // forward: y;  backward: dx
   const void* dy;    // backward
+  const void* res;   // forward: residual added before the ReLU, or NULL
   long long M;       // pixels: N * h * w
   int C;
   int rows_per_block;
@@ -164,16 +166,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const BnArgs A, co
   }
 }
 
-// F2: y = [relu](fma(x, scale, shift)); scale / shift from the stripes the statistics pass left (every thread for its own
-// channels); block 0 publishes mean / invstd and updates the running statistics.
-template <typename T, bool RELU>
-__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A, const BnFinal F) {
+// what an unfused BN kernel would have stored before the residual add read it back
+__device__ __forceinline__ float round_as(float z, float) { return z; }
+__device__ __forceinline__ float round_as(float z, __nv_bfloat16) { return __bfloat162float(__float2bfloat16_rn(z)); }
+
+// F2: y = [relu](fma(x, scale, shift) [+ residual]); scale / shift from the stripes the statistics pass left (every thread
+// for its own channels); block 0 publishes mean / invstd and updates the running statistics.  RES: the bottleneck tail
+// bn3 -> (+ shortcut) -> ReLU (networks/backbone/resnet.py:49-56) in one pass; z is rounded to T before the add, so the
+// result equals BN, add and ReLU run as three kernels bit for bit.
+template <typename T, bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads, RES ? 2 : 0) bn_apply_kernel(const BnArgs A, const BnFinal F) {
   constexpr int kCh = Vec<T>::kCh;
+  constexpr int kU = (RES && kCh == 8) ? kBnUnroll / 2 : kBnUnroll;  // two bf16 streams: 64 values in flight spill at 128 registers
   const int lpr = A.C / kCh;
   const BnThread th(lpr);
   const long long r0 = static_cast<long long>(blockIdx.x) * A.rows_per_block;
   const long long r1 = min(r0 + A.rows_per_block, A.M);
   const T* x = reinterpret_cast<const T*>(A.x);
+  const T* res = reinterpret_cast<const T*>(A.res);
   T* y = reinterpret_cast<T*>(A.y);
   for (int cb = 0; cb < lpr; cb += th.cols) {
     const int cg = cb + th.tc;
@@ -194,20 +204,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnArgs A, co
         }
       }
     }
-    for (long long r = r1 - 1 - th.tr; r >= r0; r -= static_cast<long long>(th.rpp) * kBnUnroll) {
-      float v[kBnUnroll][kCh];
+    for (long long r = r1 - 1 - th.tr; r >= r0; r -= static_cast<long long>(th.rpp) * kU) {
+      float v[kU][kCh], vr[RES ? kU : 1][kCh];
 #pragma unroll
-      for (int u = 0; u < kBnUnroll; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const long long ru = r - static_cast<long long>(u) * th.rpp;
-        if (ru >= r0) Vec<T>::load(x + ru * A.C + c0, v[u]);
+        if (ru >= r0) {
+          Vec<T>::load(x + ru * A.C + c0, v[u]);
+          if (RES) Vec<T>::load(res + ru * A.C + c0, vr[RES ? u : 0]);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < kBnUnroll; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const long long ru = r - static_cast<long long>(u) * th.rpp;
         if (ru >= r0) {
 #pragma unroll
           for (int j = 0; j < kCh; ++j) {
-            const float z = __fmaf_rn(v[u][j], scale[j], shift[j]);
+            float z = __fmaf_rn(v[u][j], scale[j], shift[j]);
+            if (RES) z = __fadd_rn(round_as(z, T()), vr[RES ? u : 0][j]);
             v[u][j] = (RELU && z < 0.f) ? 0.f : z;  // NaN passes through, as torch.relu
           }
           Vec<T>::store(y + ru * A.C + c0, v[u]);
@@ -289,6 +303,7 @@ int validate_bn(const dcfp_bn_desc* d, bool backward) {
   if (!backward) {
     DCFP_REQUIRE(d->y != nullptr && reinterpret_cast<uintptr_t>(d->y) % 16 == 0, DCFP_EINVAL, "bn_forward: y null or unaligned");
     DCFP_REQUIRE((d->running_mean == nullptr) == (d->running_var == nullptr), DCFP_EINVAL, "bn_forward: running_mean/var must come together");
+    DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->residual) % 16 == 0, DCFP_EUNSUPPORTED, "bn_forward: residual must be 16-byte aligned");
   } else {
     DCFP_REQUIRE(d->dy && d->S1 && d->S2 && d->dgamma && d->dbeta, DCFP_EINVAL, "bn_backward: null pointer (dy/S1/S2/dgamma/dbeta)");
     DCFP_REQUIRE(reinterpret_cast<uintptr_t>(d->dy) % 16 == 0 && reinterpret_cast<uintptr_t>(d->dx) % 16 == 0, DCFP_EUNSUPPORTED,
@@ -362,9 +377,16 @@ int forward_t(const dcfp_bn_desc* d, cudaStream_t stream) {
     if (rc || d->phases == 1) return rc;
   }
   A.y = d->y;
-  const BnArgs P = plan_rows<T>(A, 3, &grid);  // 73 registers / thread: 3 blocks of 256 per SM
-  if (d->relu) bn_apply_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
-  else bn_apply_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
+  A.res = d->residual;
+  const BnArgs P = plan_rows<T>(A, d->residual ? 2 : 3, &grid);  // 73 registers / thread: 3 blocks of 256 per SM (2 with the residual stream)
+  const BnFinal F = final_args(d);
+  if (d->residual) {
+    if (d->relu) bn_apply_kernel<T, true, true><<<grid, kBnThreads, 0, stream>>>(P, F);
+    else bn_apply_kernel<T, false, true><<<grid, kBnThreads, 0, stream>>>(P, F);
+  } else {
+    if (d->relu) bn_apply_kernel<T, true, false><<<grid, kBnThreads, 0, stream>>>(P, F);
+    else bn_apply_kernel<T, false, false><<<grid, kBnThreads, 0, stream>>>(P, F);
+  }
   return finish_launch("bn_apply");
 }
 
@@ -406,7 +428,7 @@ extern "C" int dcfp_bn_forward(const dcfp_bn_desc* d, void* stream_) {
     const char* e = getenv("DCFP_BN_COOP");
     return e && atoi(e) == 0;
   }();
-  if (d->workspace != nullptr && d->phases == 0 && !coop_off)
+  if (d->workspace != nullptr && d->phases == 0 && d->residual == nullptr && !coop_off)
     return d->dtype == DCFP_F32 ? coop_forward<float>(d, final_args(d), stream) : coop_forward<__nv_bfloat16>(d, final_args(d), stream);
   return d->dtype == DCFP_F32 ? forward_t<float>(d, stream) : forward_t<__nv_bfloat16>(d, stream);
 }

@@ -230,7 +230,7 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
 
 // ---- internal entry points used by bn_fused.cu ---------------------------------------------------------------------
 // BN backward, first pass: class-keyed S1/S2 of v = dz * xhat, the per-channel totals (sum dz, sum dz * xhat) into the
-// scratch stripes, and -- by the last CTA -- dgamma / dbeta and the dx coefficients (bn_common.cuh)
+// scratch stripes (bn_dx_kernel's prologue turns those into dgamma / dbeta and the dx coefficients, bn_common.cuh)
 int k1_run_bn_backward(const dcfp_layer_desc& d0, const BnFinal& fin, bool relu, float* S1f, float* S2f, cudaStream_t stream) {
   dcfp_layer_desc d = d0;
   if (S1f != nullptr) {  // fp32 rows: the fp64 pointers are unused (validate() wants them non-null)

@@ -66,11 +66,11 @@ struct NhwcParams {
 };
 // BN-backward fusion (FUSED != 0; one layer per launch): the value functor becomes v = dz * xhat with the ReLU gate
 // recomputed from the forward's own z = fma(x, zscale, zshift) (FUSED == 2), and the launch also yields the two
-// per-channel totals every BN backward needs before it can write dx:  tot[0][c] += sum dz,  tot[1][c] += sum dz * xhat.
+// per-channel totals every BN backward needs before it can write dx:  sum dz and sum dz * xhat, into the scratch stripes.
 struct NhwcFused {
   const float* gamma;  // [C]  z = fma(x, zs, zt) with zs = gamma * invstd, zt = fma(-mean, zs, beta): the SAME fp32
   const float* beta;   // [C]  expressions the forward evaluated, so the gate equals "forward output > 0" bit for bit
-  BnFinal fin;         // scratch (totals go to its stripes) + what the last CTA needs to finalise the backward
+  BnFinal fin;         // scratch: the per-channel totals go to its stripes (bn_dx_kernel turns them into dgamma / dbeta / dx)
   float* S1f;          // non-null: the class rows go to this fp32 arena with 128-bit vector reductions instead of L.S1 / L.S2
   float* S2f;
 };

@@ -413,7 +413,7 @@ bool bn_supported(int64_t N, int64_t C, int64_t h, int64_t w, bool bf16) {
 std::tuple<Tensor, Tensor, Tensor> bn_forward(const Tensor& x, const Tensor& gamma, const Tensor& beta,
                                               const optional<Tensor>& running_mean, const optional<Tensor>& running_var,
                                               Tensor sums, double momentum, double eps, bool relu, int64_t phases,
-                                              const optional<Tensor>& workspace) {
+                                              const optional<Tensor>& workspace, const optional<Tensor>& residual) {
   Tensor y = phases == 1 ? at::empty({0}, x.options()) : at::empty_like(x, x.options(), at::MemoryFormat::ChannelsLast);
   Tensor mean = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
   Tensor invstd = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
@@ -432,6 +432,13 @@ std::tuple<Tensor, Tensor, Tensor> bn_forward(const Tensor& x, const Tensor& gam
     TORCH_CHECK(workspace->is_contiguous(), "dcfp::bn_forward: workspace must be contiguous");
     d.workspace = workspace->data_ptr();
     d.workspace_bytes = static_cast<int64_t>(workspace->numel() * workspace->element_size());
+  }
+  if (residual.has_value()) {
+    require_cuda(*residual, "residual");
+    TORCH_CHECK(residual->sizes() == x.sizes() && residual->scalar_type() == x.scalar_type() &&
+                    residual->is_contiguous(at::MemoryFormat::ChannelsLast),
+                "dcfp::bn_forward: residual must match x (shape, dtype, channels_last)");
+    d.residual = residual->data_ptr();
   }
   c10::cuda::CUDAGuard guard(x.device());
   check_rc(dcfp_bn_forward(&d, cur_stream()), "bn_forward");
@@ -517,7 +524,7 @@ TORCH_LIBRARY(dcfp, m) {
   m.def("bn_scratch_bytes(int C) -> int", &bn_scratch_bytes);
   m.def("bn_workspace_bytes(int C) -> int", &bn_workspace_bytes);
   m.def("bn_forward(Tensor x, Tensor gamma, Tensor beta, Tensor(a!)? running_mean, Tensor(b!)? running_var, Tensor(c!) sums, float momentum, "
-        "float eps, bool relu, int phases=0, Tensor? workspace=None) -> (Tensor, Tensor, Tensor)",
+        "float eps, bool relu, int phases=0, Tensor? workspace=None, Tensor? residual=None) -> (Tensor, Tensor, Tensor)",
         &bn_forward);
   m.def("bn_backward(Tensor x, Tensor dy, Tensor gamma, Tensor beta, Tensor mean, Tensor invstd, Tensor? keys, Tensor(a!) S1, "
         "Tensor(b!) S2, int K, Tensor(c!) sums, bool relu, bool need_dx, int phases=0) -> (Tensor, Tensor, Tensor)",

@@ -128,12 +128,13 @@ def bn_workspace(C, device):
     return torch.empty((int(load().bn_workspace_bytes(int(C))) + 3) // 4, dtype=torch.float32, device=device)
 
 
-def bn_forward(x, gamma, beta, running_mean, running_var, sums, momentum, eps, relu, phases=0, workspace=None):
+def bn_forward(x, gamma, beta, running_mean, running_var, sums, momentum, eps, relu, phases=0, workspace=None, residual=None):
     """-> (y, mean, invstd).  sums: zeroed scratch (bn_scratch).  phases: 0 = whole call; 1 = statistics pass only
     (mean, invstd, running statistics; y is empty); 2 = normalise pass only (after a phases=1 call on the same scratch).
-    workspace (bn_workspace): with phases == 0 the forward is ONE cooperative launch (statistics + normalise)."""
+    workspace (bn_workspace): with phases == 0 the forward is ONE cooperative launch (statistics + normalise).
+    residual (same shape / dtype / layout as x): y = [relu](bn(x) + residual), the tail of a bottleneck block in one pass."""
     return load().bn_forward(x, gamma, beta, running_mean, running_var, sums, float(momentum), float(eps), bool(relu), int(phases),
-                             workspace)
+                             workspace, residual)
 
 
 def bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, K, sums, relu, need_dx=True, phases=0):

@@ -26,10 +26,13 @@ in ONE grouped K1 launch once `flush_bytes` of feature maps are pending (180 GB 
 few GB of gradients free; a grouped launch runs at ~93 % of the HBM roofline, a 16 MB single-layer
 launch at ~25-45 %).
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import ops
+from .lazy import PendingBN
 
 MAX_RESOLUTIONS = 16
 
@@ -39,10 +42,14 @@ class _FusedBN(torch.autograd.Function):
     csrc/bn_fused.cu).  Replaces nn.BatchNorm2d -> nn.ReLU(inplace=True) of the reference nets
     (networks/backbone/resnet.py:26-56, networks/tools/aspp.py:15-24) for the duration of a scoring pass.  The
     backward reads (x, dy) ONCE for everything that is a sum -- the class rows S1/S2 of the scorer's arena, dgamma
-    (their row sum: the reference's bn.weight.grad, pruners/dcfp_pruner.py:18) and dbeta -- and once more for dx."""
+    (their row sum: the reference's bn.weight.grad, pruners/dcfp_pruner.py:18) and dbeta -- and once more for dx.
+
+    residual: the shortcut of a bottleneck block (resnet.py:49-56): y = relu(bn(x) + residual) in the same element-wise
+    pass (lazy.PendingBN decides when).  The gate of that ReLU is y > 0, so the backward first forms dz = (y > 0) ? dy : 0
+    (one torch kernel, what autograd's ReLU node did before) -- the shortcut's gradient -- and runs the un-gated passes on it."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, layer, relu):
+    def forward(ctx, x, weight, bias, layer, relu, residual=None):
         sc, module = layer.scorer, layer.module
         factor = 0.0
         rm = rv = None
@@ -57,35 +64,45 @@ class _FusedBN(torch.autograd.Function):
                     module.num_batches_tracked.add_(1)
         sums_f, sums_b = sc._bn_scratch(layer)
         t = sc._t_begin()
-        y, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, workspace=sc._bn_workspace)
-        sc._t_end(t, "bn_fwd", 2 * x.numel() * x.element_size())
-        ctx.save_for_backward(x, weight, bias, mean, invstd)
-        ctx.layer, ctx.relu, ctx.sums_b = layer, relu, sums_b
+        y, mean, invstd = ops.bn_forward(x, weight, bias, rm, rv, sums_f, factor, module.eps, relu, workspace=sc._bn_workspace,
+                                         residual=residual)
+        sc._t_end(t, "bn_fwd", (2 if residual is None else 3) * x.numel() * x.element_size())
+        if residual is None:
+            ctx.save_for_backward(x, weight, bias, mean, invstd)
+        else:
+            assert relu, "a residual is only fused together with the ReLU that follows the sum"
+            sc.fused_tail_calls += 1
+            ctx.save_for_backward(x, weight, bias, mean, invstd, y)
+        ctx.layer, ctx.relu, ctx.sums_b, ctx.has_res = layer, relu, sums_b, residual is not None
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        x, weight, bias, mean, invstd = ctx.saved_tensors
+        x, weight, bias, mean, invstd = ctx.saved_tensors[:5]
         layer = ctx.layer
         sc = layer.scorer
         dy = dy.contiguous(memory_format=torch.channels_last)
+        relu = ctx.relu
+        if ctx.has_res:  # gate on the stored output; dz is the gradient of the sum: the shortcut's gradient and BN's dy
+            dy = torch.ops.aten.threshold_backward(dy, ctx.saved_tensors[5], 0)
+            relu = False
         need_dx = ctx.needs_input_grad[0]
         keys = sc._keys_for(x.shape[2], x.shape[3])
         nb = x.numel() * x.element_size()
         if sc.timing:  # the two passes timed apart: B1 (class-keyed reduction) is the path's dominant kernel
             t = sc._t_begin()
-            ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b, ctx.relu, need_dx, phases=1)
+            ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b, relu, need_dx, phases=1)
             sc._t_end(t, "bn_bwd_reduce", 2 * nb + keys.numel())
             t = sc._t_begin()
             dx, dgamma, dbeta = ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b,
-                                                ctx.relu, need_dx, phases=2)
+                                                relu, need_dx, phases=2)
             sc._t_end(t, "bn_bwd_dx", 3 * nb if need_dx else 0)
         else:
             dx, dgamma, dbeta = ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b,
-                                                ctx.relu, need_dx)
+                                                relu, need_dx)
         sc.k1_bytes += 2 * nb + keys.numel()
-        return (dx if need_dx else None), dgamma, dbeta, None, None
+        return (dx if need_dx else None), dgamma, dbeta, None, None, (dy if ctx.has_res and ctx.needs_input_grad[5] else None)
 
 
 class _FusedLayer:
@@ -126,7 +143,7 @@ def average_over_ranks(t, group=None):
 
 class ClassStatsScorer:
     def __init__(self, model, num_classes, mode="bwd", r=0.999, process_group=None, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, fused=True, track_counters=True):
+                 timing=False, fused=True, track_counters=True, fuse_residual=True):
         ops.require_gpu()
         assert mode in ("bwd", "fwd")
         self.model, self.K, self.mode, self.r = model, int(num_classes), mode, r
@@ -201,7 +218,6 @@ class ClassStatsScorer:
             # instead of the statistics + normalise kernel pair, which measures faster on every c2 layer shape
             # (13.5 vs 23 us on a 17 MB layer, 36 vs 40 us on a 67 MB one).  Its per-CTA partial sums live in this
             # unzeroed workspace shared by all layers (stream-ordered).
-            import os
             if os.environ.get("DCFP_BN_COOP", "0") == "1":
                 self._bn_workspace = ops.bn_workspace(max(sizes), self.device)
         self._views32 = {n: (self.step_arena32[0][:, a:b], self.step_arena32[1][:, a:b])
@@ -210,7 +226,11 @@ class ClassStatsScorer:
         self._fused_layers = {n: _FusedLayer(self, n, m, rows_of[n][0], rows_of[n][1], i)
                               for i, (n, m) in enumerate(self.layers)} if self.fused else {}
         self._fused_calls = {}
+        self.fused_tail_calls = 0  # fused BN calls that also added a shortcut and applied the ReLU behind it
         self._relu_after = {}  # bn name -> True once an in-place nn.ReLU was seen consuming that BN's output
+        # bn name -> True once a ReLU was seen consuming (that BN's output + something): the BN then returns a lazy.PendingBN
+        self._add_relu_after = {}
+        self.fuse_residual = bool(fuse_residual) and os.environ.get("DCFP_BN_FUSE_RESIDUAL", "1") != "0"
         self._patched = []
         self.fused_layer_calls = 0
 
@@ -238,9 +258,12 @@ class ClassStatsScorer:
             fp32 / bf16, >= 64 pixels), else its own forward (then the forward hook / K1 path scores it);
           * every nn.ReLU returns its input untouched when that input is a fused BN output that already went through
             the ReLU, and otherwise LEARNS: an in-place ReLU applied to a fused BN's output marks that BN as
-            "followed by ReLU", so from the next step on the two are one kernel.  The first step of a pass therefore
-            runs BN and ReLU apart -- with bit-identical results (same fma, same gate).  bn3 + residual add + ReLU of
-            a bottleneck stays unfused: the ReLU's input there is the sum, not a BN output."""
+            "followed by ReLU", so from the next step on the two are one kernel; a ReLU applied to (a fused BN's
+            output + another tensor) -- the tail of a bottleneck, resnet.py:49-56 -- marks that BN as "feeds a residual
+            sum", and from the next step on it returns a lazy.PendingBN, which becomes y = relu(bn(x) + shortcut) in one
+            element-wise pass when the ReLU arrives (and the plain value if anything else does).
+            The first step of a pass therefore runs BN, add and ReLU apart -- with bit-identical results (same fma,
+            same rounding before the add, same gate)."""
         sc = self
         for name, module in self.layers:
             if "forward" in module.__dict__ or not isinstance(module, nn.BatchNorm2d) or module.weight is None:
@@ -250,10 +273,17 @@ class ClassStatsScorer:
             def bn_forward(x, _m=module, _layer=layer, _name=name):
                 if not sc._eligible(_m, x):
                     return type(_m).forward(_m, x)
+                sc.fused_layer_calls += 1
+                if sc._add_relu_after.get(_name, False):
+                    def run(residual, relu, _x=x):
+                        y = _FusedBN.apply(_x, _m.weight, _m.bias, _layer, relu, residual)
+                        y._dcfp_bn = (_name, relu)
+                        return y
+
+                    return PendingBN.make(x, run, True, (_name, False))
                 relu = sc._relu_after.get(_name, False)
                 y = _FusedBN.apply(x, _m.weight, _m.bias, _layer, relu)
                 y._dcfp_bn = (_name, relu)
-                sc.fused_layer_calls += 1
                 return y
 
             module.forward = bn_forward
@@ -261,16 +291,32 @@ class ClassStatsScorer:
         for module in self.model.modules():
             if isinstance(module, nn.ReLU) and "forward" not in module.__dict__:
                 def relu_forward(inp, _m=module):
+                    if isinstance(inp, PendingBN):
+                        return inp.relu(_m.inplace)
                     tag = getattr(inp, "_dcfp_bn", None)
                     if tag is not None:
                         if tag[1]:
                             return inp  # the fused BN kernel already applied the ReLU
                         if _m.inplace:
                             sc._relu_after[tag[0]] = True
+                    elif sc.fuse_residual:
+                        sc._learn_residual_tail(inp)
                     return type(_m).forward(_m, inp)
 
                 module.forward = relu_forward
                 self._patched.append(module)
+
+    def _learn_residual_tail(self, inp):
+        """`inp` is about to go through a ReLU: if autograd says it is (fused BN output, no ReLU) + (anything), remember
+        that BN (first such operand).  Reading the graph costs nothing on the device and needs no wrapper tensors."""
+        node = getattr(inp, "grad_fn", None)
+        if node is None or type(node).__name__ != "AddBackward0" or getattr(node, "_saved_alpha", 1) != 1:
+            return
+        for fn, _ in node.next_functions:
+            layer = getattr(fn, "layer", None)  # _FusedBN's backward node carries what forward() put on ctx
+            if isinstance(layer, _FusedLayer) and layer.scorer is self and not fn.relu and not fn.has_res:
+                self._add_relu_after[layer.name] = True
+                return
 
     def _eligible(self, module, x):
         if self._labels is None or not torch.is_grad_enabled() or not (module.training or module.running_mean is None):
@@ -531,7 +577,7 @@ class ClassStatsScorer:
 
     def phase_times(self):
         """{kind: (ms, algorithmic bytes, calls)} of the fused BN passes (timing=True) -- call after a synchronize.
-        kinds: bn_fwd (statistics + normalise, one cooperative launch), bn_bwd_reduce (B1: the class-keyed reduction),
+        kinds: bn_fwd (statistics + normalise), bn_bwd_reduce (B1: the class-keyed reduction),
         bn_bwd_dx (B2)."""
         if self._phase_acc:
             return dict(self._phase_acc)
@@ -553,7 +599,8 @@ class CalibrationRun:
     all-reduce before the sign gate (the reference gates on the DDP-averaged gradient, engine.py:66)."""
 
     def __init__(self, model, num_classes, r=0.999, mode="bwd", restore_bn_stats=True, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, process_group=None, seed=None, scores_only=False, fused=True, graph=True, autocast_dtype=None):
+                 timing=False, process_group=None, seed=None, scores_only=False, fused=True, graph=True, autocast_dtype=None,
+                 fuse_residual=True):
         ops.require_gpu()
         self.model = model
         self.seed = seed
@@ -567,7 +614,7 @@ class CalibrationRun:
         # restore_bn_stats puts num_batches_tracked back at close(): the fused layers then skip its per-layer increment
         self.scorer = ClassStatsScorer(model, num_classes, mode=mode, r=r, process_group=process_group, flush_bytes=flush_bytes,
                                        keep_totals=keep_totals, timing=timing, fused=fused,
-                                       track_counters=not restore_bn_stats)
+                                       track_counters=not restore_bn_stats, fuse_residual=fuse_residual)
         self._saved = None
         self.group = process_group
         self.closed = True

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DCFP_ABI_VERSION 3
+#define DCFP_ABI_VERSION 4
 
 /* element types of feature maps / weights */
 #define DCFP_F32 0
@@ -197,8 +197,9 @@ int dcfp_class_balance_weights(const void* label, int label_dtype, int N, int H,
  *             so sum_k S1 == dgamma;  dgamma, dbeta (fp32 [C]);  dx = gamma*invstd*(dz - dbeta/M -
  *             xhat*dgamma/M) unless dx == NULL.  (x, dy) are read once for all sums, once more for dx.
  * `scratch`: caller-provided device buffer of dcfp_bn_scratch_bytes(C) bytes, 16-byte aligned, ZERO on entry
- * (fp64 partial sums striped against same-address atomic contention + the coefficient vectors the reduction
- * pass leaves for the element-wise pass + a ticket counter); one scratch per call in flight.            */
+ * (fp64 partial sums striped against same-address atomic contention, which the element-wise pass turns into its
+ * per-channel coefficients; the one-launch forward also keeps its coefficient vectors and grid-barrier flags there);
+ * one scratch per call in flight.                                                                                  */
 typedef struct dcfp_bn_desc {
   const void* x;         /* [N,h,w,C] (channels_last), dtype `dtype` */
   void* y;               /* forward out, same shape */
@@ -232,6 +233,10 @@ typedef struct dcfp_bn_desc {
                             call on the same stream (per-CTA partial sums of the one-launch forward); NULL selects the
                             two-launch forward */
   int64_t workspace_bytes;
+  const void* residual;  /* forward, or NULL: [N,h,w,C] like x, added to the normalised value BEFORE the ReLU -- the tail of a
+                            bottleneck block, bn3 -> (+ shortcut) -> ReLU (networks/backbone/resnet.py:49-56), in one pass:
+                            y = [relu](T(fma(x, scale, shift)) + residual).  The backward's gate is then y > 0: callers pass
+                            dz = (y > 0) ? dy : 0 as `dy` with relu = 0, and dz is also the shortcut's gradient */
 } dcfp_bn_desc;
 int dcfp_bn_supported(int N, int C, int h, int w, int dtype);
 size_t dcfp_bn_scratch_bytes(int C);

@@ -65,6 +65,13 @@ for C, h, w in SHAPES:
     n = 40
     t_f1 = timeit(lambda i: ops.bn_forward(xs[i % nbuf], gamma, beta, None, None, sums, 0.1, 1e-5, True, phases=1), n)
     t_f = timeit(lambda i: ops.bn_forward(xs[i % nbuf], gamma, beta, None, None, sums, 0.1, 1e-5, True), n)
+    # bottleneck tail: bn -> (+ shortcut) -> ReLU in the normalise pass, against the same three steps as three kernels
+    t_fr = timeit(lambda i: ops.bn_forward(xs[i % nbuf], gamma, beta, None, None, sums, 0.1, 1e-5, True, residual=dys[i % nbuf]), n)
+
+    def apart(i):
+        z, _, _ = ops.bn_forward(xs[i % nbuf], gamma, beta, None, None, sums, 0.1, 1e-5, False)
+        torch.relu_(z + dys[i % nbuf])
+    t_fa = timeit(apart, n)
     wsp = ops.bn_workspace(C, dev)
 
     def coop(i):
@@ -77,6 +84,6 @@ for C, h, w in SHAPES:
     t_k1 = timeit(lambda i: ops.class_stats(xs[i % nbuf], keys, R, S1, S2, dy=dys[i % nbuf], scale=invstd, shift=mean, affine_mode=1), n)
     gb = lambda us, mult: mult * nbytes / us / 1e3
     print("C=%4d %3dx%3d %6.1f MB | F1 %6.1f us %5.0f GB/s | F1+F2 %6.1f us (alg 2x: %5.0f GB/s) | coopF %6.1f us (alg 2x: %5.0f GB/s) | B1 %6.1f us %5.0f GB/s | K1bwd %6.1f us | "
-          "B1+B2 %6.1f us (alg 3x: %5.0f GB/s) | ideal@peak F %.1f B %.1f us" %
-          (C, h, w, nbytes / 1e6, t_f1, gb(t_f1, 1), t_f, gb(t_f, 2), t_c, gb(t_c, 2), t_b1, gb(t_b1, 2), t_k1, t_b, gb(t_b, 3),
+          "B1+B2 %6.1f us (alg 3x: %5.0f GB/s) | tail fused %6.1f us (alg 3x: %5.0f GB/s) vs bn, add, relu apart %6.1f us | ideal@peak F %.1f B %.1f us" %
+          (C, h, w, nbytes / 1e6, t_f1, gb(t_f1, 1), t_f, gb(t_f, 2), t_c, gb(t_c, 2), t_b1, gb(t_b1, 2), t_k1, t_b, gb(t_b, 3), t_fr, gb(t_fr, 3), t_fa,
            2 * nbytes / PEAK / 1e3, 3 * nbytes / PEAK / 1e3), flush=True)

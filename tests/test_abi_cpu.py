@@ -29,10 +29,10 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_struct_layout(lib):
-    assert lib.dcfp_abi_version() == 3
+    assert lib.dcfp_abi_version() == 4
     assert ctypes.sizeof(abi.LayerDesc) == 7 * 8 + 10 * 4
     assert ctypes.sizeof(abi.GatherDesc) == 4 * 8 + 4 * 4
-    assert ctypes.sizeof(abi.BnDesc) == 16 * 8 + 8 * 4 + 2 * 4 + 2 * 4 + 2 * 8  # struct dcfp_bn_desc
+    assert ctypes.sizeof(abi.BnDesc) == 16 * 8 + 8 * 4 + 2 * 4 + 2 * 4 + 3 * 8  # struct dcfp_bn_desc
     assert lib.dcfp_bn_scratch_bytes(256) >= 4 * 2 * 256 * 8 + 5 * 256 * 4 and lib.dcfp_bn_workspace_bytes(256) > 0
     assert lib.dcfp_bn_supported(2, 256, 64, 128, abi.F32) == 1 and lib.dcfp_bn_supported(2, 30, 64, 128, abi.F32) == 0
     assert lib.dcfp_channel_gather_workspace(10) >= 10 * ctypes.sizeof(abi.GatherDesc) + 11 * 8

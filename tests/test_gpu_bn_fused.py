@@ -183,6 +183,53 @@ def test_bf16_forward_backward(native):
     assert ((S1.sum(0) - dgamma.double()).abs() <= 1e-6 * dgamma.abs().max()).all()
 
 
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_with_residual_equals_bn_add_relu_run_apart(native, shape, dtype):
+    """y = relu(bn(x) + residual) in one element-wise pass (dcfp_bn_desc.residual; the bottleneck tail of
+    networks/backbone/resnet.py:49-56): BIT-identical to the library's BN followed by torch's add and ReLU (z is rounded to
+    the map's dtype before the add), and within the forward tolerance of the fp64 composition."""
+    from dcfp_b200 import ops
+    N, C, h, w, K = shape
+    if dtype == torch.bfloat16 and C % 8:
+        pytest.skip("bf16 maps need C % 8 == 0")
+    x, r, gamma, beta = _inputs(N, C, h, w, seed=C + h + 1, offset=1.0)
+    r = (r * 1e3).to(dtype)  # _inputs scales its second tensor like a gradient; a shortcut has the size of an activation
+    x = x.to(dtype)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    y, mean, invstd = ops.bn_forward(x, gamma, beta, rm, rv, ops.bn_scratch(C, DEV), 0.1, 1e-5, True, residual=r)
+    z, mean0, invstd0 = ops.bn_forward(x, gamma, beta, None, None, ops.bn_scratch(C, DEV), 0.1, 1e-5, False)
+    torch.cuda.synchronize()
+    assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    _close(mean, mean0, 1e-6, "mean")  # the statistics come from atomics in two different orders
+    if torch.equal(mean, mean0) and torch.equal(invstd, invstd0):
+        assert torch.equal(y, torch.relu(z + r))
+    else:  # (rare) a last-bit difference in a channel's statistics: compare the channels whose coefficients agree
+        same = (mean == mean0) & (invstd == invstd0)
+        assert same.float().mean() > 0.9
+        assert torch.equal(y[:, same], torch.relu(z + r)[:, same])
+    y64 = torch.relu(torch.nn.functional.batch_norm(x.double(), None, None, gamma.double(), beta.double(), True, 0.1, 1e-5) + r.double())
+    _close(y.float(), y64, 1e-5 if dtype == torch.float32 else 1.5e-2, "y vs fp64")
+    var, mu = torch.var_mean(x.double(), dim=(0, 2, 3), unbiased=False)
+    _close(rm, 0.1 * mu, 1e-6, "running_mean")
+    # without the ReLU (not used by the scorer, part of the ABI)
+    y2, _, _ = ops.bn_forward(x, gamma, beta, None, None, ops.bn_scratch(C, DEV), 0.1, 1e-5, False, residual=r)
+    y64n = torch.nn.functional.batch_norm(x.double(), None, None, gamma.double(), beta.double(), True, 0.1, 1e-5) + r.double()
+    _close(y2.float(), y64n, 1e-5 if dtype == torch.float32 else 1.5e-2, "y (no relu) vs fp64")
+
+
+def test_forward_residual_is_validated(native):
+    from dcfp_b200 import ops
+    x, r, gamma, beta = _inputs(2, 64, 16, 16, seed=3)
+    sums = ops.bn_scratch(64, DEV)
+    with pytest.raises(RuntimeError):
+        ops.bn_forward(x, gamma, beta, None, None, sums, 0.1, 1e-5, True, residual=r.contiguous())  # NCHW residual
+    with pytest.raises(RuntimeError):
+        ops.bn_forward(x, gamma, beta, None, None, sums, 0.1, 1e-5, True, residual=r.bfloat16())
+    with pytest.raises(RuntimeError):
+        ops.bn_forward(x, gamma, beta, None, None, sums, 0.1, 1e-5, True, residual=r[:, :, :8])
+
+
 def test_rejects_unsupported_inputs(native):
     from dcfp_b200 import ops
     x = torch.randn(2, 64, 16, 16, device=DEV)  # NCHW

@@ -4,7 +4,8 @@ running on dcfp's own forward / backward, the class rows coming out of the BN ba
     with the unfused (cuDNN BN + hook + deferred K1) pass of the same model on the same micro-batches,
   * sum over the class rows == the bn.weight.grad autograd hands out (now both produced by one kernel: exact to fp32),
   * the model is left untouched: modules unpatched, running statistics and counters restored,
-  * which layers fuse with their ReLU (bn1 / bn2 of a bottleneck: yes; bn3 before the residual add: no).
+  * which layers fuse with their ReLU (bn1 / bn2 of a bottleneck) and which with the residual add + ReLU behind them (bn3:
+    the lazy.PendingBN protocol, tests/test_lazy_bn_cpu.py), and that the latter changes nothing but the kernel count.
 """
 import numpy as np
 import pytest
@@ -30,9 +31,9 @@ def _batch(idx, classes=K):
     return x.to(DEV).contiguous(memory_format=torch.channels_last), y.to(DEV)
 
 
-def _run(model, classes, fused, steps=3, keep_grads=False):
+def _run(model, classes, fused, steps=3, keep_grads=False, fuse_residual=True):
     from dcfp_b200.scorer import CalibrationRun
-    run = CalibrationRun(model, classes, r=0.999, seed=5, fused=fused)
+    run = CalibrationRun(model, classes, r=0.999, seed=5, fused=fused, fuse_residual=fuse_residual)
     losses, grads = [], None
     for s in range(steps):
         x, y = _batch([2 * s, 2 * s + 1], classes)
@@ -42,7 +43,8 @@ def _run(model, classes, fused, steps=3, keep_grads=False):
     sc = run.scorer
     eic = sc.eic.cpu().numpy().copy()
     totals = sc.totals.cpu().clone()
-    info = dict(fused_calls=sc.fused_layer_calls, relu_after=dict(sc._relu_after))
+    info = dict(fused_calls=sc.fused_layer_calls, relu_after=dict(sc._relu_after), add_relu_after=dict(sc._add_relu_after),
+                tail_calls=sc.fused_tail_calls)
     run.close()
     return losses, eic, totals, grads, info
 
@@ -105,6 +107,42 @@ def test_which_layers_fuse_with_their_relu(native):
     assert "backbone.layer1.0.bn3" not in ra and "backbone.layer1.0.downsample.1" not in ra  # residual add comes first
     assert ra.get("aspp.aspp1.bn") and ra.get("last_conv.1")
     assert "aspp.bn1" not in ra  # in ignore_prune_layer: not scored, so it stays torch's BatchNorm
+    # bn3 -> (+ shortcut) -> ReLU: learned in step 1, one fused call per bottleneck in step 2 (ResNet-50: 16 blocks)
+    ar = info["add_relu_after"]
+    assert ar.get("backbone.layer1.0.bn3") and ar.get("backbone.layer3.5.bn3") and ar.get("backbone.layer4.2.bn3")
+    assert "backbone.layer1.0.downsample.1" not in ar and "backbone.layer1.0.bn1" not in ar
+    assert len(ar) == 16 and info["tail_calls"] == 16, (len(ar), info["tail_calls"])
+    _, _, _, _, off = _run(model, K, fused=True, steps=2, fuse_residual=False)
+    assert off["add_relu_after"] == {} and off["tail_calls"] == 0
+
+
+def test_residual_tail_fusion_changes_no_result(native):
+    """Same model, same micro-batches, IEEE fp32 convolutions: with and without the fused bn3 + shortcut + ReLU tail the
+    losses agree to fp32 round-off, and gradients / pass totals differ by no more than two runs of the SAME program do
+    (statistics and sums come from atomics, whose order changes from run to run; a random-init net amplifies that)."""
+    model = _model(seed=3)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        l0, e0, t0, g0, i0 = _run(model, K, fused=True, steps=3, keep_grads=True, fuse_residual=False)
+        l2, e2, t2, g2, i2 = _run(model, K, fused=True, steps=3, keep_grads=True, fuse_residual=False)
+        l1, e1, t1, g1, i1 = _run(model, K, fused=True, steps=3, keep_grads=True, fuse_residual=True)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert i1["tail_calls"] == 32 and i0["tail_calls"] == 0 and i0["fused_calls"] == i1["fused_calls"]
+    assert np.allclose(l0, l1, rtol=2e-6), (l0, l1)
+
+    def dist(ga, gb):
+        return np.array([float((ga[n] - gb[n]).abs().max() / (gb[n].abs().max() + 1e-30)) for n in gb])
+
+    d_same, d_tail = dist(g2, g0), dist(g1, g0)
+    assert np.median(d_tail) <= 3.0 * np.median(d_same) + 1e-5 and d_tail.max() <= 3.0 * d_same.max() + 1e-3, \
+        (np.median(d_tail), np.median(d_same), d_tail.max(), d_same.max())
+    tot_same = np.abs(t2.numpy() - t0.numpy()).sum() / np.abs(t0.numpy()).sum()
+    tot_tail = np.abs(t1.numpy() - t0.numpy()).sum() / np.abs(t0.numpy()).sum()
+    assert tot_tail <= 3.0 * tot_same + 1e-5, (tot_tail, tot_same)
+    print("gradient distance to a reference run: same program median %.3g max %.3g | fused tail median %.3g max %.3g; totals %.3g | %.3g"
+          % (np.median(d_same), d_same.max(), np.median(d_tail), d_tail.max(), tot_same, tot_tail))
 
 
 def test_row_sums_are_the_gradient_autograd_hands_out(native):
