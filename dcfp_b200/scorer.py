@@ -91,6 +91,9 @@ class _FusedBN(torch.autograd.Function):
         keys = sc._keys_for(x.shape[2], x.shape[3])
         nb = x.numel() * x.element_size()
         if sc.timing:  # the two passes timed apart: B1 (class-keyed reduction) is the path's dominant kernel
+            # an EMPTY event pair first: what two consecutive event records cost on this stream (inside a graph: one node
+            # transition), so that a reader -- bench.py's roofline -- can take it out of the bracketed kernel times
+            sc._t_end(sc._t_begin(), "event_pair", 0)
             t = sc._t_begin()
             ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b, relu, need_dx, phases=1)
             sc._t_end(t, "bn_bwd_reduce", 2 * nb + keys.numel())
@@ -577,8 +580,8 @@ class ClassStatsScorer:
 
     def phase_times(self):
         """{kind: (ms, algorithmic bytes, calls)} of the fused BN passes (timing=True) -- call after a synchronize.
-        kinds: bn_fwd (statistics + normalise), bn_bwd_reduce (B1: the class-keyed reduction),
-        bn_bwd_dx (B2)."""
+        kinds: bn_fwd (statistics + normalise), bn_bwd_reduce (B1: the class-keyed reduction), bn_bwd_dx (B2), event_pair
+        (an empty bracket recorded in front of every B1 bracket: the cost of the timing events themselves)."""
         if self._phase_acc:
             return dict(self._phase_acc)
         out = {}
