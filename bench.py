@@ -540,6 +540,13 @@ def run_b200_arm(args, c):
     main["run"].sync_scores()
     value = K * mb * world / (main["ms"] * 1e-3)
     roofline = roofline_of(main, K, mb, ctx.nhwc)
+    # the path as a whole: algorithmic bytes of ALL its passes (F1 + F2 + B1 + B2 [+ deferred K1]) over the sum of their bracketed
+    # times -- raw brackets, nothing subtracted.  Second reads of a map that the 126 MB L2 still holds count as algorithmic bytes.
+    ph = {k: v for k, v in main["phases"].items() if k != "event_pair"}
+    p_gb, p_ms = sum(v["algorithmic_gb_per_step"] for v in ph.values()), sum(v["ms_per_step"] for v in ph.values())
+    if p_ms > 0:
+        roofline["whole_path"] = {"algorithmic_gb_per_step": p_gb, "ms_per_step": p_ms, "achieved_gbs": p_gb / (p_ms * 1e-3),
+                                  "frac": p_gb / (p_ms * 1e-3) / roofline["peak"], "passes": sorted(ph)}
     sc.all_reduce_totals()  # the single end-of-pass statistics all-reduce (outside the per-step timing, reported below)
     allreduce_ms = 0.0
     if world > 1:
