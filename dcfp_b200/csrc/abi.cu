@@ -2,7 +2,6 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -38,14 +37,6 @@ int finish_launch(const char* what) {
   if (e != cudaSuccess) return cuda_fail(e, what);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
-}
-
-bool pdl_enabled() {
-  static const bool on = []() {
-    const char* e = getenv("DCFP_PDL");
-    return e != nullptr && atoi(e) != 0;
-  }();
-  return on;
 }
 
 int num_sms() {

@@ -108,7 +108,6 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const BnArgs A, const BnFinal F) {
   constexpr int kCh = Vec<T>::kCh;
   __shared__ float red[kBnThreads * 2 * kCh];
-  pdl_launch_dependents();  // bn_apply_kernel may become resident now; it waits for this grid before it reads the stripes
   const int lpr = A.C / kCh;
   const int cols = min(lpr, kStatCols);
   const int rpp = kBnThreads / cols;
@@ -186,7 +185,6 @@ __global__ void __launch_bounds__(kBnThreads, RES ? 2 : 0) bn_apply_kernel(const
   const T* x = reinterpret_cast<const T*>(A.x);
   const T* res = reinterpret_cast<const T*>(A.res);
   T* y = reinterpret_cast<T*>(A.y);
-  pdl_wait();  // the statistics pass in front of this launch has completed and its stripes are visible
   for (int cb = 0; cb < lpr; cb += th.cols) {
     const int cg = cb + th.tc;
     if (!th.active || cg >= lpr) continue;
@@ -245,7 +243,6 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A, co
   const T* x = reinterpret_cast<const T*>(A.x);
   const T* dy = reinterpret_cast<const T*>(A.dy);
   T* dx = reinterpret_cast<T*>(A.y);
-  pdl_wait();  // B1 in front of this launch has completed and its stripes are visible
   for (int cb = 0; cb < lpr; cb += th.cols) {
     const int cg = cb + th.tc;
     if (!th.active || cg >= lpr) continue;
@@ -383,10 +380,13 @@ int forward_t(const dcfp_bn_desc* d, cudaStream_t stream) {
   A.res = d->residual;
   const BnArgs P = plan_rows<T>(A, d->residual ? 2 : 3, &grid);  // 73 registers / thread: 3 blocks of 256 per SM (2 with the residual stream)
   const BnFinal F = final_args(d);
-  void (*apply)(BnArgs, BnFinal) = d->residual ? (d->relu ? bn_apply_kernel<T, true, true> : bn_apply_kernel<T, false, true>)
-                                               : (d->relu ? bn_apply_kernel<T, true, false> : bn_apply_kernel<T, false, false>);
-  const cudaError_t e = launch_after_primary(apply, grid, dim3(kBnThreads), 0, stream, P, F);
-  if (e != cudaSuccess) return cuda_fail(e, "bn_apply");
+  if (d->residual) {
+    if (d->relu) bn_apply_kernel<T, true, true><<<grid, kBnThreads, 0, stream>>>(P, F);
+    else bn_apply_kernel<T, false, true><<<grid, kBnThreads, 0, stream>>>(P, F);
+  } else {
+    if (d->relu) bn_apply_kernel<T, true, false><<<grid, kBnThreads, 0, stream>>>(P, F);
+    else bn_apply_kernel<T, false, false><<<grid, kBnThreads, 0, stream>>>(P, F);
+  }
   return finish_launch("bn_apply");
 }
 
@@ -398,9 +398,8 @@ int backward_dx_t(const dcfp_bn_desc* d, cudaStream_t stream) {
   dim3 grid;
   const BnArgs P = plan_rows<T>(A, 2, &grid);
   if (d->dx == nullptr) grid = dim3(1);  // gradients of gamma / beta only
-  void (*dxk)(BnArgs, BnFinal) = d->relu ? bn_dx_kernel<T, true> : bn_dx_kernel<T, false>;
-  const cudaError_t e = launch_after_primary(dxk, grid, dim3(kBnThreads), 0, stream, P, final_args(d));
-  if (e != cudaSuccess) return cuda_fail(e, "bn_dx");
+  if (d->relu) bn_dx_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
+  else bn_dx_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(P, final_args(d));
   return finish_launch("bn_dx");
 }
 

@@ -15,30 +15,6 @@ int cuda_fail(cudaError_t e, const char* what);
 // opt a kernel into > 48 KB dynamic shared memory once per (kernel, device)
 int ensure_smem(const void* func, int bytes);
 
-// Programmatic dependent launch (sm_90+).  A kernel launched with launch_after_primary() may become resident while the
-// kernel in front of it on the stream is still running; it must not touch that kernel's results before pdl_wait().  The
-// primary allows it from the moment all its CTAs have executed pdl_launch_dependents() (or exited).  Both are no-ops for
-// ordinary launches.  Used for the two-kernel BN passes (statistics -> normalise, reduction -> dx): the second kernel's
-// launch latency overlaps the first kernel instead of following it.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// DCFP_PDL=1 (read once): launch the second kernel of a pair as a programmatic dependent
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_after_primary(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 constexpr int kNumSMs = 148;  // B200 (compile-time default for table sizing)
 // SM count of the current device (queried once per device; persistent grids are sized with it)
 int num_sms();

@@ -137,12 +137,6 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(slots + kNhwcWarps * kNhwcSlots * 256);
 
   K1_TRACE(0);
-  if (FUSED) pdl_launch_dependents();  // bn_dx_kernel may become resident; it waits for this grid before it reads the stripes
-  if (FUSED && (threadIdx.x & 31) == 0) {  // per-layer launch: the two descriptors every warp's first TMA needs, fetched while
-                                           // the barriers / slot rows are set up
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.maps[0])) : "memory");
-    if (BWD) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.maps[1])) : "memory");
-  }
   const unsigned K = static_cast<unsigned>(P.K);
   const int n_tiles = P.tile_prefix[P.n_layers];
   const int t_first = static_cast<int>(static_cast<long long>(blockIdx.x) * n_tiles / gridDim.x);
