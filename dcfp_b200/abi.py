@@ -72,6 +72,7 @@ def load(path=LIB_PATH):
     lib.dcfp_bn_workspace_bytes.argtypes = [i32]
     lib.dcfp_bn_forward.argtypes = [ctypes.POINTER(BnDesc), vp]
     lib.dcfp_bn_backward.argtypes = [ctypes.POINTER(BnDesc), vp]
+    lib.dcfp_relu_grad.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     lib.dcfp_eic_update.argtypes = [vp, vp, vp, i32, vp, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_eic_update_flat.argtypes = [vp, vp, vp, i32, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.dcfp_reduce_classes.argtypes = [vp, i32, i32, vp, vp]

@@ -286,6 +286,55 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_dx_kernel(const BnArgs A, co
   }
 }
 
+// ReLU backward of the bottleneck tail with the gradient accumulation in front of it folded in:
+//   dz = (y > 0) ? dy [+ dy2] : 0
+// dy2 is the shortcut gradient the NEXT block hands back (its own dz): autograd would first add it to the gradient arriving
+// through conv1 (read 2, write 1) and then gate the sum (read 2, write 1); here the sum never exists (read 3, write 1).
+// Grid-stride over 16-byte vectors; bit-identical to torch's add followed by threshold_backward.
+template <typename T, bool ADD>
+__global__ void __launch_bounds__(kBnThreads) relu_grad_kernel(const T* __restrict__ y, const T* __restrict__ dy, const T* __restrict__ dy2,
+                                                               T* __restrict__ dz, long long n_vec) {
+  constexpr int kCh = Vec<T>::kCh;
+  constexpr int kU = 2;
+  const long long stride = static_cast<long long>(gridDim.x) * kBnThreads;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBnThreads + threadIdx.x; i < n_vec; i += stride * kU) {
+    float vy[kU][kCh], va[kU][kCh], vb[ADD ? kU : 1][kCh];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long iu = i + u * stride;
+      if (iu < n_vec) {
+        Vec<T>::load(y + iu * kCh, vy[u]);
+        Vec<T>::load(dy + iu * kCh, va[u]);
+        if (ADD) Vec<T>::load(dy2 + iu * kCh, vb[ADD ? u : 0]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long iu = i + u * stride;
+      if (iu < n_vec) {
+#pragma unroll
+        for (int j = 0; j < kCh; ++j) {
+          const float g = ADD ? __fadd_rn(va[u][j], vb[ADD ? u : 0][j]) : va[u][j];
+          va[u][j] = vy[u][j] <= 0.f ? 0.f : g;  // torch's threshold_backward: (self <= threshold) ? 0 : grad (a NaN y passes grad)
+        }
+        Vec<T>::store(dz + iu * kCh, va[u]);
+      }
+    }
+  }
+}
+
+template <typename T>
+int relu_grad_t(const void* y, const void* dy, const void* dy2, void* dz, long long n, cudaStream_t stream) {
+  const long long n_vec = n / Vec<T>::kCh;
+  const long long want = (n_vec + 2LL * kBnThreads - 1) / (2LL * kBnThreads);
+  const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want, 8LL * num_sms())));
+  if (dy2) relu_grad_kernel<T, true><<<grid, kBnThreads, 0, stream>>>(static_cast<const T*>(y), static_cast<const T*>(dy),
+                                                                       static_cast<const T*>(dy2), static_cast<T*>(dz), n_vec);
+  else relu_grad_kernel<T, false><<<grid, kBnThreads, 0, stream>>>(static_cast<const T*>(y), static_cast<const T*>(dy), nullptr,
+                                                                   static_cast<T*>(dz), n_vec);
+  return finish_launch("relu_grad");
+}
+
 int validate_bn(const dcfp_bn_desc* d, bool backward) {
   DCFP_REQUIRE(d != nullptr, DCFP_EINVAL, "bn: null descriptor");
   DCFP_REQUIRE(d->x && d->gamma && d->beta && d->mean && d->invstd && d->scratch, DCFP_EINVAL, "bn: null pointer (x/gamma/beta/mean/invstd/scratch)");
@@ -461,4 +510,17 @@ extern "C" int dcfp_bn_backward(const dcfp_bn_desc* d, void* stream_) {
     if (rc || d->phases == 1) return rc;
   }
   return d->dtype == DCFP_F32 ? backward_dx_t<float>(d, stream) : backward_dx_t<__nv_bfloat16>(d, stream);
+}
+
+extern "C" int dcfp_relu_grad(const void* y, const void* dy, const void* dy2, void* dz, int64_t n, int dtype, void* stream_) {
+  using namespace dcfp;
+  DCFP_REQUIRE(y && dy && dz && n > 0, DCFP_EINVAL, "relu_grad: null pointer or empty tensor");
+  DCFP_REQUIRE(dtype == DCFP_F32 || dtype == DCFP_BF16, DCFP_EINVAL, "relu_grad: unknown dtype %d", dtype);
+  const int kch = dtype == DCFP_F32 ? 4 : 8;
+  DCFP_REQUIRE(n % kch == 0, DCFP_EUNSUPPORTED, "relu_grad: n=%lld must be a multiple of %d", static_cast<long long>(n), kch);
+  DCFP_REQUIRE(reinterpret_cast<uintptr_t>(y) % 16 == 0 && reinterpret_cast<uintptr_t>(dy) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(dy2) % 16 == 0 && reinterpret_cast<uintptr_t>(dz) % 16 == 0,
+               DCFP_EUNSUPPORTED, "relu_grad: pointers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return dtype == DCFP_F32 ? relu_grad_t<float>(y, dy, dy2, dz, n, stream) : relu_grad_t<__nv_bfloat16>(y, dy, dy2, dz, n, stream);
 }

@@ -493,6 +493,27 @@ std::tuple<Tensor, Tensor, Tensor> bn_backward(const Tensor& x, const Tensor& dy
   return {dx, dgamma, dbeta};
 }
 
+// dz = (y > 0) ? dy (+ dy2) : 0; the tensors share shape, dtype and (dense) layout
+Tensor relu_grad(const Tensor& y, const Tensor& dy, const optional<Tensor>& dy2) {
+  require_cuda(y, "y");
+  require_cuda(dy, "dy");
+  TORCH_CHECK(y.scalar_type() == at::kFloat || y.scalar_type() == at::kBFloat16, "dcfp::relu_grad: fp32 or bf16 tensors");
+  TORCH_CHECK(y.is_non_overlapping_and_dense() && dy.sizes() == y.sizes() && dy.strides() == y.strides() && dy.scalar_type() == y.scalar_type(),
+              "dcfp::relu_grad: dy must match y (shape, strides, dtype), dense");
+  if (dy2.has_value()) {
+    require_cuda(*dy2, "dy2");
+    TORCH_CHECK(dy2->sizes() == y.sizes() && dy2->strides() == y.strides() && dy2->scalar_type() == y.scalar_type(),
+                "dcfp::relu_grad: dy2 must match y (shape, strides, dtype)");
+  }
+  Tensor dz = at::empty_like(y);  // preserves the (dense) strides
+  TORCH_CHECK(dz.strides() == y.strides(), "dcfp::relu_grad: could not allocate an output with the input's layout");
+  c10::cuda::CUDAGuard guard(y.device());
+  check_rc(dcfp_relu_grad(y.data_ptr(), dy.data_ptr(), dy2.has_value() ? dy2->data_ptr() : nullptr, dz.data_ptr(), y.numel(),
+                          y.scalar_type() == at::kFloat ? DCFP_F32 : DCFP_BF16, cur_stream()),
+           "relu_grad");
+  return dz;
+}
+
 int64_t launch_count(bool reset) { return dcfp_launch_count(reset ? 1 : 0); }
 int64_t abi_version() { return dcfp_abi_version(); }
 
@@ -529,6 +550,7 @@ TORCH_LIBRARY(dcfp, m) {
   m.def("bn_backward(Tensor x, Tensor dy, Tensor gamma, Tensor beta, Tensor mean, Tensor invstd, Tensor? keys, Tensor(a!) S1, "
         "Tensor(b!) S2, int K, Tensor(c!) sums, bool relu, bool need_dx, int phases=0) -> (Tensor, Tensor, Tensor)",
         &bn_backward);
+  m.def("relu_grad(Tensor y, Tensor dy, Tensor? dy2=None) -> Tensor", &relu_grad);
   m.def("launch_count(bool reset) -> int", &launch_count);
   m.def("abi_version() -> int", &abi_version);
 }

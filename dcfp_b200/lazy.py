@@ -104,3 +104,31 @@ class PendingBN(torch.Tensor):
 
         args, kwargs = tree_map(real, (tuple(args), dict(kwargs)))
         return func(*args, **kwargs)
+
+
+# ---- the same tail in the backward pass: the shortcut gradient handed straight to the block that produced the shortcut -------
+#
+# y_prev --+--> conv1 -> ... -> bn3 --(+)--> ReLU --> y          backward:  dz = relu'(y) * dy  is BOTH bn3's gradient and the
+#          +---------- shortcut ------^                                    shortcut's; autograd adds the latter to the gradient
+#                                                                          arriving at y_prev through conv1 (read 2, write 1),
+# and the previous block then gates that sum with relu'(y_prev) (read 2, write 1).  When y_prev was itself produced by a fused
+# tail, the consumer can instead DEPOSIT dz on the producer's backward node and report "no gradient" for the shortcut; the
+# producer folds the deposit into its own gate kernel: dz_prev = relu'(y_prev) * (dy + deposit) -- read 3, write 1, no sum tensor.
+# autograd runs a node only after every consumer of its outputs has run, so the deposit is always there in time.
+
+def deposit_shortcut_grad(producer_node, grad, ledger):
+    """Called by the consumer's backward instead of returning `grad` for its shortcut input.  `ledger`: a one-element list
+    counting open deposits, checked at the end of the step (an unconsumed deposit would be a silently lost gradient)."""
+    held = getattr(producer_node, "_dcfp_deposit", None)
+    producer_node._dcfp_deposit = grad if held is None else held + grad
+    if held is None:
+        ledger[0] += 1
+
+
+def take_shortcut_grad(node, ledger):
+    """Called at the top of the producer's backward: the deposited gradient, or None."""
+    held = getattr(node, "_dcfp_deposit", None)
+    if held is not None:
+        node._dcfp_deposit = None
+        ledger[0] -= 1
+    return held

@@ -143,6 +143,12 @@ def bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, K, sums, relu, n
     return load().bn_backward(x, dy, gamma, beta, mean, invstd, keys, S1, S2, int(K), sums, bool(relu), bool(need_dx), int(phases))
 
 
+def relu_grad(y, dy, dy2=None):
+    """dz = (y > 0) ? dy (+ dy2) : 0 -- the ReLU backward behind a residual sum, with the accumulation of the block input's two
+    gradients folded in (dy2: the shortcut gradient handed back by the next block).  Same values as torch's add + threshold_backward."""
+    return load().relu_grad(y, dy, dy2)
+
+
 # ---- K2 ----------------------------------------------------------------------------------------
 def r_pair(r):
     """(float32(r), float32(1 - r)) exactly as `eic*r + g*(1-r)` sees them (dcfp_pruner.py:20)."""

@@ -32,7 +32,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .lazy import PendingBN
+from .lazy import PendingBN, deposit_shortcut_grad, take_shortcut_grad
 
 MAX_RESOLUTIONS = 16
 
@@ -49,7 +49,7 @@ class _FusedBN(torch.autograd.Function):
     (one torch kernel, what autograd's ReLU node did before) -- the shortcut's gradient -- and runs the un-gated passes on it."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, layer, relu, residual=None):
+    def forward(ctx, x, weight, bias, layer, relu, residual=None, res_node=None):
         sc, module = layer.scorer, layer.module
         factor = 0.0
         rm = rv = None
@@ -74,6 +74,9 @@ class _FusedBN(torch.autograd.Function):
             sc.fused_tail_calls += 1
             ctx.save_for_backward(x, weight, bias, mean, invstd, y)
         ctx.layer, ctx.relu, ctx.sums_b, ctx.has_res = layer, relu, sums_b, residual is not None
+        # res_node: the backward node of the fused tail that PRODUCED the residual (the previous bottleneck): this block's
+        # shortcut gradient is deposited there instead of going through autograd's accumulation (lazy.deposit_shortcut_grad)
+        ctx.res_node = res_node if (residual is not None and ctx.needs_input_grad[5]) else None
         return y
 
     @staticmethod
@@ -84,9 +87,14 @@ class _FusedBN(torch.autograd.Function):
         sc = layer.scorer
         dy = dy.contiguous(memory_format=torch.channels_last)
         relu = ctx.relu
+        deposit = take_shortcut_grad(ctx, sc._deposits)  # the next block's shortcut gradient, if it was handed over directly
         if ctx.has_res:  # gate on the stored output; dz is the gradient of the sum: the shortcut's gradient and BN's dy
-            dy = torch.ops.aten.threshold_backward(dy, ctx.saved_tensors[5], 0)
+            t = sc._t_begin()
+            dy = ops.relu_grad(ctx.saved_tensors[5], dy, deposit)
+            sc._t_end(t, "tail_relu_bwd", (3 if deposit is None else 4) * x.numel() * x.element_size())
             relu = False
+        elif deposit is not None:
+            dy = dy + deposit
         need_dx = ctx.needs_input_grad[0]
         keys = sc._keys_for(x.shape[2], x.shape[3])
         nb = x.numel() * x.element_size()
@@ -105,7 +113,13 @@ class _FusedBN(torch.autograd.Function):
             dx, dgamma, dbeta = ops.bn_backward(x, dy, weight, bias, mean, invstd, keys, layer.S1, layer.S2, sc.rows, ctx.sums_b,
                                                 relu, need_dx)
         sc.k1_bytes += 2 * nb + keys.numel()
-        return (dx if need_dx else None), dgamma, dbeta, None, None, (dy if ctx.has_res and ctx.needs_input_grad[5] else None)
+        gres = None
+        if ctx.has_res and ctx.needs_input_grad[5]:
+            if ctx.res_node is not None:
+                deposit_shortcut_grad(ctx.res_node, dy, sc._deposits)
+            else:
+                gres = dy
+        return (dx if need_dx else None), dgamma, dbeta, None, None, gres, None
 
 
 class _FusedLayer:
@@ -233,6 +247,7 @@ class ClassStatsScorer:
         self._relu_after = {}  # bn name -> True once an in-place nn.ReLU was seen consuming that BN's output
         # bn name -> True once a ReLU was seen consuming (that BN's output + something): the BN then returns a lazy.PendingBN
         self._add_relu_after = {}
+        self._deposits = [0]  # open shortcut-gradient deposits (lazy.deposit_shortcut_grad); must be 0 after a backward pass
         self.fuse_residual = bool(fuse_residual) and os.environ.get("DCFP_BN_FUSE_RESIDUAL", "1") != "0"
         self._patched = []
         self.fused_layer_calls = 0
@@ -279,7 +294,10 @@ class ClassStatsScorer:
                 sc.fused_layer_calls += 1
                 if sc._add_relu_after.get(_name, False):
                     def run(residual, relu, _x=x):
-                        y = _FusedBN.apply(_x, _m.weight, _m.bias, _layer, relu, residual)
+                        node = getattr(residual, "grad_fn", None)
+                        if not (isinstance(node, _FusedBN._backward_cls) and node.has_res and node.layer.scorer is sc):
+                            node = None  # the shortcut was not produced by a fused tail: its gradient goes through autograd
+                        y = _FusedBN.apply(_x, _m.weight, _m.bias, _layer, relu, residual, node)
                         y._dcfp_bn = (_name, relu)
                         return y
 
@@ -308,6 +326,13 @@ class ClassStatsScorer:
 
                 module.forward = relu_forward
                 self._patched.append(module)
+
+    def check_deposits(self):
+        """After a backward pass: every shortcut gradient a fused tail handed to its producer must have been consumed."""
+        if self._deposits[0] != 0:
+            n, self._deposits[0] = self._deposits[0], 0
+            raise RuntimeError("dcfp_b200: %d shortcut gradient(s) deposited on a fused BN tail were never consumed (that tail's "
+                               "backward did not run); score this model with fuse_residual=False" % n)
 
     def _learn_residual_tail(self, inp):
         """`inp` is about to go through a ReLU: if autograd says it is (fused BN output, no ReLU) + (anything), remember
@@ -527,6 +552,7 @@ class ClassStatsScorer:
     def fold_step(self):
         """End of one step: flush deferred layers, then ONE launch yields dgamma = sum_k S1 (fp32 [sumC]),
         adds the step arena into the pass totals and zeroes it for the next step."""
+        self.check_deposits()
         self.flush()
         return ops.fold_step(self.step_arena, self.totals, self.step_arena32)
 
@@ -580,7 +606,8 @@ class ClassStatsScorer:
 
     def phase_times(self):
         """{kind: (ms, algorithmic bytes, calls)} of the fused BN passes (timing=True) -- call after a synchronize.
-        kinds: bn_fwd (statistics + normalise), bn_bwd_reduce (B1: the class-keyed reduction), bn_bwd_dx (B2), event_pair
+        kinds: bn_fwd (statistics + normalise), bn_bwd_reduce (B1: the class-keyed reduction), bn_bwd_dx (B2), tail_relu_bwd
+        (ReLU backward + gradient fan-in of a bottleneck tail), event_pair
         (an empty bracket recorded in front of every B1 bracket: the cost of the timing events themselves)."""
         if self._phase_acc:
             return dict(self._phase_acc)
@@ -692,6 +719,7 @@ class CalibrationRun:
         loss = out["loss"] if isinstance(out, dict) else out
         if sc.mode == "bwd":
             loss.backward()
+            sc.check_deposits()
         return sc.fold_step(), loss.detach().float()
 
     def _capture(self, key, x, y):

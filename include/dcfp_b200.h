@@ -243,6 +243,11 @@ size_t dcfp_bn_scratch_bytes(int C);
 size_t dcfp_bn_workspace_bytes(int C);
 int dcfp_bn_forward(const dcfp_bn_desc* desc_host, void* stream);
 int dcfp_bn_backward(const dcfp_bn_desc* desc_host, void* stream);
+/* ReLU backward behind a residual sum (the gate of dcfp_bn_desc.residual), with the gradient accumulation autograd would
+ * run in front of it folded in:  dz[i] = y[i] > 0 ? dy[i] (+ dy2[i]) : 0  over n elements of `dtype` (any layout: the
+ * four tensors share one).  dy2 may be NULL.  Bit-identical to torch's add followed by threshold_backward
+ * (networks/backbone/resnet.py:55-56 in reverse: ReLU, then the fan-in of the block input's two gradients).          */
+int dcfp_relu_grad(const void* y, const void* dy, const void* dy2, void* dz, int64_t n, int dtype, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------- */
 const char* dcfp_last_error(void);

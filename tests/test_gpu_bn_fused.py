@@ -230,6 +230,33 @@ def test_forward_residual_is_validated(native):
         ops.bn_forward(x, gamma, beta, None, None, sums, 0.1, 1e-5, True, residual=r[:, :, :8])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_dy2", [False, True])
+def test_relu_grad_equals_add_then_threshold_backward(native, dtype, with_dy2):
+    """dcfp_relu_grad: dz = (y > 0) ? dy (+ dy2) : 0, bit-identical to torch's add followed by threshold_backward -- zeros,
+    negative zeros and NaNs in y included (a NaN y passes the gradient, as torch does)."""
+    from dcfp_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    shape = (3, 40, 9, 7)  # 7560 elements: a ragged last vector block for neither dtype (n % 8 == 0), odd rows
+    y = torch.relu(torch.randn(shape, generator=g)).to(DEV).contiguous(memory_format=torch.channels_last)
+    y.view(-1)[::97] = float("nan")
+    y.view(-1)[1::89] = -0.0
+    y = y.to(dtype)
+    dy = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last).to(dtype)
+    dy2 = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last).to(dtype) if with_dy2 else None
+    dz = ops.relu_grad(y, dy, dy2)
+    ref = torch.ops.aten.threshold_backward(dy + dy2 if with_dy2 else dy, y, 0)
+    assert dz.dtype == dtype and dz.stride() == y.stride()
+    assert torch.equal(torch.nan_to_num(dz.float(), nan=12345.0), torch.nan_to_num(ref.float(), nan=12345.0))
+    big = torch.randn(2, 1024, 64, 128, device=DEV).contiguous(memory_format=torch.channels_last)  # a c2 map: the grid-stride loop
+    gb = torch.randn_like(big)
+    assert torch.equal(ops.relu_grad(big, gb, gb), torch.ops.aten.threshold_backward(gb + gb, big, 0))
+    with pytest.raises(RuntimeError):
+        ops.relu_grad(y, dy.contiguous())  # different strides
+    with pytest.raises(RuntimeError):
+        ops.relu_grad(y, dy, dy[:, :8])
+
+
 def test_rejects_unsupported_inputs(native):
     from dcfp_b200 import ops
     x = torch.randn(2, 64, 16, 16, device=DEV)  # NCHW

@@ -226,3 +226,83 @@ def test_reference_bottleneck_tail_is_one_fused_call():
         torch.testing.assert_close(out, ref_out, rtol=1e-6, atol=1e-6)
         for g, r in zip(grads, ref_grads):
             torch.testing.assert_close(g, r, rtol=1e-5, atol=1e-6)
+
+
+# ---- the backward half: shortcut gradients deposited on the producing tail's node (lazy.deposit_shortcut_grad) ---------------
+class _Tail(torch.autograd.Function):
+    """y = relu(a * x + res) with scorer._FusedBN's deposit protocol (a toy stand-in for bn3 + shortcut + ReLU)."""
+
+    @staticmethod
+    def forward(ctx, x, res, a, res_node, ledger, log):
+        y = torch.relu(a * x + res)
+        ctx.save_for_backward(y)
+        ctx.a, ctx.ledger, ctx.log, ctx.has_res = a, ledger, log, True
+        ctx.res_node = res_node if ctx.needs_input_grad[1] else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from dcfp_b200.lazy import deposit_shortcut_grad, take_shortcut_grad
+        (y,) = ctx.saved_tensors
+        dep = take_shortcut_grad(ctx, ctx.ledger)
+        ctx.log.append("fused" if dep is not None else "plain")
+        dz = (dy if dep is None else dy + dep) * (y > 0)
+        gres = None
+        if ctx.res_node is not None:
+            deposit_shortcut_grad(ctx.res_node, dz, ctx.ledger)
+        elif ctx.needs_input_grad[1]:
+            gres = dz
+        return ctx.a * dz, gres, None, None, None, None
+
+
+def _tower(x0, ws, deposit):
+    ledger, log = [0], []
+    t = x0 * 1.0
+    for w in ws:
+        branch = torch.sin(t) * w  # the conv1 .. bn3 path of a block
+        if deposit is None:
+            t = torch.relu(0.7 * branch + t)
+        else:
+            node = t.grad_fn if (deposit and isinstance(t.grad_fn, _Tail._backward_cls)) else None
+            t = _Tail.apply(branch, t, 0.7, node, ledger, log)
+    return t, ledger, log
+
+
+def test_deposited_shortcut_gradients_equal_autograd_accumulation():
+    torch.manual_seed(0)
+    x0 = torch.randn(4, 6, dtype=torch.float64)
+    ws0 = [torch.randn(6, dtype=torch.float64) for _ in range(5)]
+    weight = torch.randn(4, 6, dtype=torch.float64)
+    res = {}
+    for mode in (None, False, True):
+        x = x0.clone().requires_grad_(True)
+        ws = [w.clone().requires_grad_(True) for w in ws0]
+        out, ledger, log = _tower(x, ws, mode)
+        (out * weight).sum().backward()
+        res[mode] = [x.grad] + [w.grad for w in ws]
+        assert ledger[0] == 0
+        if mode:  # backward order: the last block has no consumer that deposits; the four before it fold a deposit into their gate
+            assert log == ["plain"] + ["fused"] * 4, log
+        elif mode is False:
+            assert log == ["plain"] * 5
+    for a, b, c in zip(res[None], res[False], res[True]):
+        torch.testing.assert_close(b, a, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(c, a, rtol=1e-12, atol=1e-12)
+
+
+def test_unconsumed_deposit_is_detected():
+    """A tail whose output feeds ONLY a shortcut: autograd may never run (or run with zeros) the producer -- the ledger says so."""
+    from dcfp_b200.scorer import ClassStatsScorer
+
+    class Sc:
+        _deposits = [0]
+    ledger, log = Sc._deposits, []
+    x = torch.randn(3, dtype=torch.float64, requires_grad=True)
+    z = torch.randn(3, dtype=torch.float64, requires_grad=True)
+    t1 = _Tail.apply(x * 1.0, x * 0.5, 0.7, None, ledger, log)
+    t2 = _Tail.apply(z * 1.0, t1.detach().requires_grad_(True), 0.7, t1.grad_fn, ledger, log)  # graph cut: t1's node never runs
+    t2.sum().backward()
+    assert ledger[0] == 1
+    with pytest.raises(RuntimeError, match="never consumed"):
+        ClassStatsScorer.check_deposits(Sc)
+    assert Sc._deposits[0] == 0
