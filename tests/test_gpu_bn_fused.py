@@ -239,8 +239,9 @@ def test_relu_grad_equals_add_then_threshold_backward(native, dtype, with_dy2):
     g = torch.Generator().manual_seed(11)
     shape = (3, 40, 9, 7)  # 7560 elements: a ragged last vector block for neither dtype (n % 8 == 0), odd rows
     y = torch.relu(torch.randn(shape, generator=g)).to(DEV).contiguous(memory_format=torch.channels_last)
-    y.view(-1)[::97] = float("nan")
-    y.view(-1)[1::89] = -0.0
+    flat = y.permute(0, 2, 3, 1).view(-1)  # the channels_last storage in memory order
+    flat[::97] = float("nan")
+    flat[1::89] = -0.0
     y = y.to(dtype)
     dy = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last).to(dtype)
     dy2 = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last).to(dtype) if with_dy2 else None
