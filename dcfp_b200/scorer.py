@@ -160,7 +160,7 @@ def average_over_ranks(t, group=None):
 
 class ClassStatsScorer:
     def __init__(self, model, num_classes, mode="bwd", r=0.999, process_group=None, flush_bytes=1 << 30, keep_totals=True,
-                 timing=False, fused=True, track_counters=True, fuse_residual=True):
+                 timing=False, fused=True, track_counters=True, fuse_residual=True, shadow_unscored=True):
         ops.require_gpu()
         assert mode in ("bwd", "fwd")
         self.model, self.K, self.mode, self.r = model, int(num_classes), mode, r
@@ -226,9 +226,17 @@ class ClassStatsScorer:
         # fused BN: one scratch per layer and direction (striped fp64 partial sums + coefficient vectors, csrc/bn_common.cuh),
         # all of them in one flat buffer zeroed once per step
         self._bn_ws = self._bn_workspace = None
+        # BatchNorm2d layers the reference does NOT score (ignore_prune_layer: the last bottleneck's bn3, the ASPP / deep-supervision
+        # heads) run on the same kernels -- they are part of the same forward / backward pass over the same kind of maps -- with
+        # their class rows going to a scratch arena nobody reads
+        scored = {id(m) for _, m in self.layers}
+        self._shadow = [(n, m) for n, m in model.named_modules()
+                        if type(m) is nn.BatchNorm2d and id(m) not in scored and m.weight is not None and m.weight.numel() % 4 == 0
+                        and m.weight.device == self.device] if (self.fused and shadow_unscored) else []
+        self._dump = None
         if self.fused:
             self._bn_ws_off = [0]
-            for c in sizes:
+            for c in sizes + [m.weight.numel() for _, m in self._shadow]:
                 self._bn_ws_off.append(self._bn_ws_off[-1] + ops.bn_scratch_elems(c))
             self._bn_ws = torch.zeros(2 * self._bn_ws_off[-1], dtype=torch.float64, device=self.device)
             # DCFP_BN_COOP=1: the one-launch cooperative forward (bit-reproducible statistics, no atomics; csrc/bn_coop.cuh)
@@ -242,6 +250,12 @@ class ClassStatsScorer:
         rows_of = self._views32 if self.step_arena32 is not None else self._views
         self._fused_layers = {n: _FusedLayer(self, n, m, rows_of[n][0], rows_of[n][1], i)
                               for i, (n, m) in enumerate(self.layers)} if self.fused else {}
+        if self._shadow:
+            cmax = max(m.weight.numel() for _, m in self._shadow)
+            self._dump = torch.zeros(2, R, cmax, dtype=torch.float32 if self.step_arena32 is not None else torch.float64, device=self.device)
+            for i, (n, m) in enumerate(self._shadow):
+                c = m.weight.numel()
+                self._fused_layers[n] = _FusedLayer(self, n, m, self._dump[0][:, :c], self._dump[1][:, :c], len(self.layers) + i)
         self._fused_calls = {}
         self.fused_tail_calls = 0  # fused BN calls that also added a shortcut and applied the ReLU behind it
         self._relu_after = {}  # bn name -> True once an in-place nn.ReLU was seen consuming that BN's output
@@ -283,7 +297,7 @@ class ClassStatsScorer:
             The first step of a pass therefore runs BN, add and ReLU apart -- with bit-identical results (same fma,
             same rounding before the add, same gate)."""
         sc = self
-        for name, module in self.layers:
+        for name, module in self.layers + self._shadow:
             if "forward" in module.__dict__ or not isinstance(module, nn.BatchNorm2d) or module.weight is None:
                 continue
             layer = self._fused_layers[name]
@@ -403,6 +417,8 @@ class ClassStatsScorer:
         if self._bn_ws is not None:
             self._bn_ws.zero_()
             self._fused_calls = {}
+            if self._dump is not None:
+                self._dump.zero_()
 
     def _keys_for(self, h, w):
         key = (h, w)

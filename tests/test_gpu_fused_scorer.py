@@ -106,13 +106,13 @@ def test_which_layers_fuse_with_their_relu(native):
     assert ra.get("backbone.layer1.0.bn1") and ra.get("backbone.layer1.0.bn2") and ra.get("backbone.bn1")
     assert "backbone.layer1.0.bn3" not in ra and "backbone.layer1.0.downsample.1" not in ra  # residual add comes first
     assert ra.get("aspp.aspp1.bn") and ra.get("last_conv.1")
-    assert "aspp.bn1" not in ra  # in ignore_prune_layer: not scored, so it stays torch's BatchNorm
-    # bn3 -> (+ shortcut) -> ReLU: learned in step 1, one fused call per bottleneck in step 2 (ResNet-50: 16 blocks, of which
-    # layer4.2.bn3 is in ignore_prune_layer -- not scored, torch's BatchNorm)
+    assert ra.get("aspp.bn1")  # in ignore_prune_layer: not scored, but run by the same kernels (class rows to a scratch arena)
+    # bn3 -> (+ shortcut) -> ReLU: learned in step 1, one fused call per bottleneck in step 2 (ResNet-50: 16 blocks; the last
+    # one, layer4.2.bn3, is in ignore_prune_layer -- unscored, same kernels)
     ar = info["add_relu_after"]
-    assert ar.get("backbone.layer1.0.bn3") and ar.get("backbone.layer3.5.bn3") and ar.get("backbone.layer4.1.bn3")
-    assert "backbone.layer1.0.downsample.1" not in ar and "backbone.layer1.0.bn1" not in ar and "backbone.layer4.2.bn3" not in ar
-    assert len(ar) == 15 and info["tail_calls"] == 15, (len(ar), info["tail_calls"])
+    assert ar.get("backbone.layer1.0.bn3") and ar.get("backbone.layer3.5.bn3") and ar.get("backbone.layer4.2.bn3")
+    assert "backbone.layer1.0.downsample.1" not in ar and "backbone.layer1.0.bn1" not in ar
+    assert len(ar) == 16 and info["tail_calls"] == 16, (len(ar), info["tail_calls"])
     _, _, _, _, off = _run(model, K, fused=True, steps=2, fuse_residual=False)
     assert off["add_relu_after"] == {} and off["tail_calls"] == 0
 
@@ -130,7 +130,7 @@ def test_residual_tail_fusion_changes_no_result(native):
         l1, e1, t1, g1, i1 = _run(model, K, fused=True, steps=3, keep_grads=True, fuse_residual=True)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
-    assert i1["tail_calls"] == 30 and i0["tail_calls"] == 0 and i0["fused_calls"] == i1["fused_calls"]
+    assert i1["tail_calls"] == 32 and i0["tail_calls"] == 0 and i0["fused_calls"] == i1["fused_calls"]
     assert np.allclose(l0, l1, rtol=2e-6), (l0, l1)
 
     def dist(ga, gb):
