@@ -176,10 +176,26 @@ int run(const dcfp_layer_desc* descs, int n_layers, cudaStream_t stream) {
     plan.single_wave = n_nhwc == 1;
     plan.keep_l2 = (descs[nhwc[0]].hints & DCFP_HINT_KEEP_L2) != 0;
     const int nhwc_big = bwd ? kNhwcBigGroupBwd : kNhwcBigGroupFwd;
+    // forward functor on bf16 maps: 16-warp CTAs (k1_nhwc.cuh) -- measured [B200], all c2 layers of 2 images in one grouped
+    // launch: bf16 51 % -> 80 % of the HBM roofline, fp32 95 % -> 94 % (already bandwidth-bound: stays on 8 warps); at
+    // K = 150 neither kernel is bound by its streaming loop (35 % both).  DCFP_K1_FWD_WARPS=8|16 forces one kernel for
+    // both dtypes (A/B measurements, and the GPU suite's second pass over the forward cases).
+    static const int forced_warps = []() {
+      const char* e = getenv("DCFP_K1_FWD_WARPS");
+      return e ? atoi(e) : 0;
+    }();
+    const int fwd_warps = forced_warps ? forced_warps : (dtype == DCFP_BF16 ? kNhwcFwdWarpsBf16 : kNhwcWarps);
     for (int first = 0; first < n_nhwc;) {
       const int m = std::min(n_nhwc - first, nhwc_big);
       int rc;
-      if (m <= kSmallGroup) {
+      if (!bwd && fwd_warps == 16) {
+        if (m <= kSmallGroup)
+          rc = dtype == DCFP_F32 ? run_nhwc<float, false, kSmallGroup, 0, 16>(descs, nhwc + first, m, plan, stream)
+                                 : run_nhwc<__nv_bfloat16, false, kSmallGroup, 0, 16>(descs, nhwc + first, m, plan, stream);
+        else
+          rc = dtype == DCFP_F32 ? run_nhwc<float, false, kNhwcBigGroupFwd, 0, 16>(descs, nhwc + first, m, plan, stream)
+                                 : run_nhwc<__nv_bfloat16, false, kNhwcBigGroupFwd, 0, 16>(descs, nhwc + first, m, plan, stream);
+      } else if (m <= kSmallGroup) {
         if (dtype == DCFP_F32)
           rc = bwd ? run_nhwc<float, true, kSmallGroup>(descs, nhwc + first, m, plan, stream)
                    : run_nhwc<float, false, kSmallGroup>(descs, nhwc + first, m, plan, stream);

@@ -36,7 +36,17 @@ constexpr int kNhwcSlab = 128;       // channels per warp row: 32 lanes x 4
 constexpr int kNhwcSlots = 12;       // class rows per warp (tag of row i lives in lane i)
 // one staged box = [G px][128 ch]: 8 KB fp32 forward (G = 16), 4 KB bf16 forward (G = 16), 4 KB per tensor backward:
 // 8 KB per pipeline stage either way, so the fixed per-iteration work (wait, key broadcast, refill) is paid per 8 KB
-__host__ __device__ constexpr int nhwc_box_bytes(bool bwd, int elem_size = 4) { return (bwd || elem_size == 2) ? 4096 : 8192; }
+__host__ __device__ constexpr int nhwc_box_bytes(bool bwd, int elem_size = 4, int warps = 8) {
+  return (bwd || elem_size == 2 || warps > 8) ? 4096 : 8192;
+}
+// 16-warp variant (forward functor): 16 warps x (2 x 4 KB stages + 6 class rows) -- twice the warps per scheduler to hide the
+// instruction latency of the accumulation chain (ncu on the 8-warp bf16 forward kernel: 2 warps per scheduler at ~5.5 cycles
+// per instruction each, issue active 33 %, 23 instructions per 128-channel pixel row).  The 96 row tags a CTA can publish at
+// a fold are the same (16 x 6 = 8 x 12).  (Outlining the cold eviction path with __noinline__ was tried as well: hook-path
+// kernels 8 000 -> 6 500 instructions, but the per-layer kernels of the fused BN backward grew and every variant needed
+// 16-25 more registers for the call ABI -- dropped.)
+constexpr int kNhwcTagsPerCta = kNhwcWarps * kNhwcSlots;
+constexpr int kNhwcFwdWarpsBf16 = 16;  // forward functor, bf16 maps (fp32 maps: kNhwcWarps)
 
 struct NhwcLayer {
   const uint8_t* keys;  // [N*HW]
@@ -100,7 +110,7 @@ struct BoxRow<__nv_bfloat16> {
   static constexpr int kLaneBytes = 8;
 };
 
-constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp: 4 x-boxes, or 2 (x, dy) pairs
+constexpr int kNhwcStageBudget = 16 << 10;  // bytes of staging per warp (8-warp CTAs): 4 x-boxes, or 2 (x, dy) pairs; 16-warp CTAs: half
 
 // -DDCFP_K1_TRACE (DCFP_K1_TRACE=1 python -m dcfp_b200.build): thread 0 of every CTA of the fused instantiation stamps
 // %globaltimer at seven points of the kernel (scripts/k1_trace.py prints the per-phase times: this is how the merge tree
@@ -120,11 +130,14 @@ __device__ __forceinline__ unsigned long long gtime() {
 // FOLD2: -1 = per layer at run time (grouped launches); 0 / 1 = known at compile time (the per-layer launches of the fused BN
 // backward: half of the accumulation code disappears -- the kernel is ~6 000 SASS instructions, and a launch that runs for
 // 12 us starts with a cold instruction cache every time)
-template <typename T, bool BWD, bool AFFINE, int MAXL, int FUSED = 0, int FOLD2 = -1>
-__global__ void __launch_bounds__(kNhwcWarps * 32, 1)
+template <typename T, bool BWD, bool AFFINE, int MAXL, int FUSED = 0, int FOLD2 = -1, int WARPS = kNhwcWarps>
+__global__ void __launch_bounds__(WARPS * 32, 1)
     class_stats_nhwc_kernel(const __grid_constant__ NhwcParams<MAXL, BWD ? 2 : 1> P, const NhwcFused F) {
   static_assert(FUSED == 0 || BWD, "the fused BN-backward functor reads x and dy");
-  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)));
+  static_assert(WARPS == 8 || WARPS == 16, "8 or 16 warps per CTA");
+  constexpr int kNhwcWarps = WARPS;                    // shadow the namespace-scope defaults inside the kernel
+  constexpr int kNhwcSlots = kNhwcTagsPerCta / WARPS;  // 12 or 6 class rows per warp
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)), WARPS);
   constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   constexpr int Q = G / 4;  // packed key words (4 pixels each) per group
   constexpr int kTens = BWD ? 2 : 1;
@@ -459,11 +472,10 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, 1)
       }
     };
     unsigned kcur[2 * Q], knxt[2 * Q], kw[2 * Q];
+    K1_TRACE(1);
+    for (int s = 0; s < kStages; ++s) issue();  // the first boxes go out before anything else of the tile is fetched
     fetch_keys(0, kcur);
     fetch_keys(32, knxt);
-
-    K1_TRACE(1);
-    for (int s = 0; s < kStages; ++s) issue();
     if (new_slab) {  // per-channel coefficients of the slab: loaded AFTER the first boxes are in flight (their global-load
                      // latency used to sit in front of the first TMA issue: ~1 us of a 17 us launch)
       sc01 = sc23 = pack2(1.f, 1.f);
@@ -659,11 +671,14 @@ struct NhwcPlan {
   bool keep_l2 = false;
 };
 
-template <typename T, bool BWD, int MAXL, int FUSED = 0>
+template <typename T, bool BWD, int MAXL, int FUSED = 0, int WARPS = kNhwcWarps>
 int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPlan& plan, cudaStream_t stream,
              const NhwcFused* fused = nullptr) {
+  static_assert(WARPS == kNhwcWarps || (!BWD && FUSED == 0), "16-warp CTAs: forward functor only (one 4 KB box per stage)");
+  constexpr int kNhwcWarps = WARPS;
+  constexpr int kNhwcSlots = kNhwcTagsPerCta / WARPS;
   constexpr int kTens = BWD ? 2 : 1;
-  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)));
+  constexpr int kNhwcBoxBytes = nhwc_box_bytes(BWD, static_cast<int>(sizeof(T)), WARPS);
   constexpr int G = kNhwcBoxBytes / BoxRow<T>::kRowBytes;
   const int K = descs[which[0]].K;
   const int sms = num_sms();
@@ -675,7 +690,11 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPl
     const char* e = getenv("DCFP_K1_NO_CONTIG");
     return e ? atoi(e) : 0;
   }();
-  P.contig = (plan.single_wave && !no_contig) ? 1 : 0;
+  static const int force_contig = []() {
+    const char* e = getenv("DCFP_K1_FORCE_CONTIG");
+    return e ? atoi(e) : 0;
+  }();
+  P.contig = ((plan.single_wave && !no_contig) || force_contig) ? 1 : 0;
   static const int skip_rows = []() {
     const char* e = getenv("DCFP_K1_DEBUG_SKIP_ROWS");
     return e ? atoi(e) : 0;
@@ -746,8 +765,9 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPl
     const char* e = getenv("DCFP_K1_NHWC_STAGES");
     return e ? atoi(e) : 0;
   }();
-  P.stages = kNhwcStageBudget / (kTens * kNhwcBoxBytes);
-  if (forced >= 1 && forced * kTens * kNhwcBoxBytes <= (20 << 10)) P.stages = forced;
+  constexpr int kBudget = kNhwcStageBudget * 8 / WARPS;  // staging bytes per warp
+  P.stages = kBudget / (kTens * kNhwcBoxBytes);
+  if (forced >= 1 && forced * kTens * kNhwcBoxBytes <= kBudget + (kBudget >> 2)) P.stages = forced;
   static const int force_keep = []() {
     const char* e = getenv("DCFP_K1_KEEP_L2");
     return e ? atoi(e) : -1;
@@ -756,8 +776,8 @@ int run_nhwc(const dcfp_layer_desc* descs, const int* which, int n, const NhwcPl
   const size_t smem = static_cast<size_t>(kNhwcWarps) * P.stages * kTens * kNhwcBoxBytes +
                       static_cast<size_t>(kNhwcWarps) * kNhwcSlots * 256 * sizeof(float) + 8 * kNhwcWarps * P.stages +
                       1024 /* base alignment slack */;
-  void (*kern)(NhwcParams<MAXL, kTens>, NhwcFused) = class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED>;
-  if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL, 0>;
+  void (*kern)(NhwcParams<MAXL, kTens>, NhwcFused) = class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED, -1, WARPS>;
+  if (!BWD && !affine) kern = class_stats_nhwc_kernel<T, BWD, false, MAXL, 0, -1, WARPS>;
   if (FUSED) kern = P.L[0].fold2 ? class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED, (FUSED ? 1 : -1)>
                                  : class_stats_nhwc_kernel<T, BWD, true, MAXL, FUSED, (FUSED ? 0 : -1)>;
   NhwcFused F{};

@@ -35,6 +35,11 @@ class _Nvtx:
 
 
 
+# warps per CTA of the NHWC forward-functor kernel on bf16 maps (kNhwcFwdWarpsBf16 in csrc/k1_nhwc.cuh; fp32 maps: 8;
+# DCFP_K1_FWD_WARPS=8|16 forces one kernel for both dtypes)
+K1_FWD_WARPS_BF16 = 16
+
+
 def load():
     """Registers torch.ops.dcfp.* (idempotent)."""
     global _loaded

@@ -11,7 +11,7 @@ dev = torch.device("cuda")
 K = int(os.environ.get("K", 19))
 mb = 2
 H0, W0 = (512, 1024) if K == 19 else (512, 512)
-_, lab = synthetic_batch([0, 1], K, H0, W0)
+_, lab = synthetic_batch([0, 1], K, H0, W0, fragmentation=os.environ.get("FRAG") or None)
 lab = lab.to(dev)
 KEYS = {}
 def keys_for(shapes):

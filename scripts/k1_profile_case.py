@@ -11,7 +11,7 @@ K = int(os.environ.get("K", 19))
 bwd = os.environ.get("BWD", "0") == "1"
 dtype = torch.bfloat16 if os.environ.get("DT", "f32") == "bf16" else torch.float32
 S = 1 if K == 19 else 2  # 512x1024 (Cityscapes) vs 512x512 (ADE / COCO-Stuff) label maps
-_, lab = synthetic_batch([0, 1], K, 512, 1024 // S)
+_, lab = synthetic_batch([0, 1], K, 512, 1024 // S, fragmentation=os.environ.get("FRAG") or None)
 lab = lab.to(dev)
 KEYS = {}
 def keys_for(shapes):

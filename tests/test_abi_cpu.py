@@ -97,3 +97,15 @@ def test_no_product_module_imports_the_oracle():
     code = "import sys; import dcfp_b200.scorer, dcfp_b200.pruners.dcfp_pruner, dcfp_b200.pruners.random_pruner; " \
            "assert not [m for m in sys.modules if m.split('.')[0] == 'oracle']"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
+
+
+def test_python_constants_match_the_kernel_headers():
+    """ops.K1_FWD_WARPS_BF16 mirrors kNhwcFwdWarpsBf16."""
+    import re
+
+    from dcfp_b200 import ops
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "dcfp_b200", "csrc", "k1_nhwc.cuh")).read()
+    m = re.search(r"constexpr int kNhwcFwdWarpsBf16 = (\d+);", src)
+    assert m and int(m.group(1)) == ops.K1_FWD_WARPS_BF16

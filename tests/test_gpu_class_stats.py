@@ -536,3 +536,21 @@ def test_randomized_grouped_launches_on_a_shared_arena(native, seed):
         e2 = (A2[:, p:p + C].cpu() - r2).abs()
         assert (e2 <= 4 * RTOL * r2 + 1e-30).all(), "columns %d:%d S2 max rel err %.3g" % (p, p + C, (e2 / (r2 + 1e-30)).max())
     assert (A1.cpu()[:, ~own] == 3.0).all() and (A2.cpu()[:, ~own] == 3.0).all(), "wrote outside the layers' columns"
+
+
+@pytest.mark.parametrize("warps", ["8", "16"])
+def test_forward_kernel_with_a_forced_warp_count(native, warps):
+    """The forward functor has an 8-warp and a 16-warp NHWC kernel (default: 16 for bf16 maps, 8 for fp32;
+    DCFP_K1_FWD_WARPS, read once per process, forces one for both): the channels_last / randomized / shared-arena cases
+    above run again in a child process with each, so both dtypes are checked on both kernels."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, DCFP_K1_FWD_WARPS=warps)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                           "-k", "(channels_last or randomized or shared_arena or maximum_class or more_layers or fwd_matches) "
+                                 "and not forced_warp_count"],
+                          cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-3000:]
