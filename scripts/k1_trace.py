@@ -1,6 +1,6 @@
 """Per-phase timeline of the fused K1 kernel (B1): needs a trace build -- DCFP_K1_TRACE=1 python -m dcfp_b200.build -- whose CTAs
 stamp %globaltimer at seven points (csrc/k1_nhwc.cuh: K1_TRACE).  Prints mean / max over the CTAs of one launch per shape."""
-import ctypes, sys, os
+import ctypes, sys
 sys.path.insert(0, ".")
 import numpy as np, torch
 from dcfp_b200 import ops, abi

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from dcfp_b200 import ops
-from oracle import eic_ref, gather_ref, mask_ref
+from oracle import eic_ref, gather_ref
 
 
 def _thresh_mask(score, layer_off, layer_group, min_keep, k0, k1):

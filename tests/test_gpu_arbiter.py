@@ -8,7 +8,6 @@ the class rows S1[k, c] = sum_{p in class k} dy * xhat and their row sum dgamma 
     up to 2.6e5 terms that cancel to ~1/400 of their mass; its error relative to the MASS is what is comparable).
 
 c2 at its full size (DeepLabV3-R101, 512x1024), a handful of layers of every shape class."""
-import numpy as np
 import pytest
 import torch
 
