@@ -80,7 +80,7 @@ class PendingBN(torch.Tensor):
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         name = _name(func)
-        if name in _META:
+        if name in _META and not (name == "type" and (len(args) > 1 or kwargs)):  # t.type(dtype) converts VALUES: resolve first
             with torch._C.DisableTorchFunctionSubclass():
                 return func(*args, **kwargs)
         if name in _ADD and len(args) == 2 and (not kwargs or (list(kwargs) == ["alpha"] and kwargs["alpha"] == 1)):

@@ -169,6 +169,11 @@ def test_placeholder_answers_metadata_without_resolving():
     q = p + _cl(torch.randn(2, 8, 4, 3))
     assert isinstance(q, PendingBN) and q.shape == x.shape and calls == []
     assert getattr(q, "_dcfp_bn") == ("bn", False)
+    # ... but `type` WITH an argument is a conversion of the values, not a metadata read: it must see the layer's output
+    assert p.type() == "torch.FloatTensor" and calls == []
+    z = p.type(torch.float64)
+    assert calls == [(False, False)] and type(z) is torch.Tensor
+    torch.testing.assert_close(z, _eager(x, bn).double())
 
 
 def test_residual_tail_is_learned_from_the_autograd_graph():
