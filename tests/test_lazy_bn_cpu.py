@@ -109,6 +109,12 @@ PROGRAMS = {
     "strided_residual": (lambda p, r: F.relu(p + r.contiguous()), [(False, False)]),
     "broadcast_residual": (lambda p, r: F.relu(p + r[:, :, :1, :1]), [(False, False)]),
     "double_add": (lambda p, r: F.relu((p + r) + r), [(False, False)]),
+    "conv_consumer": (lambda p, r: F.conv2d(p, torch.full((8, 8, 1, 1), 0.125)) + r, [(False, False)]),
+    "sub_materializes": (lambda p, r: F.relu(p - r), [(False, False)]),
+    "dtype_conversion": (lambda p, r: F.relu(p.double() + r.double()).float(), [(False, False)]),
+    "type_conversion": (lambda p, r: F.relu(p.type(torch.float64) + r.double()).float(), [(False, False)]),
+    "view_then_add": (lambda p, r: F.relu(p.view_as(r) + r), [(False, False)]),
+    "tail_plus_detached_bn_output": (lambda p, r: F.relu(p + r) + p.detach(), [(True, True), (False, False)]),
     "metadata_only": (lambda p, r: F.relu(p + r) * float(p.shape[1] + p.dim() + p.size(0) + int(p.is_contiguous(memory_format=torch.channels_last))),
                       [(True, True)]),
 }
