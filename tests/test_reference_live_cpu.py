@@ -180,3 +180,90 @@ def test_random_pruner_live_reference_same_rng_stream():
             sb, cb = pm.prune_model(copy.deepcopy(base), except_start_keys=["conv_deepsup"])
         assert all(np.array_equal(ca[k]["out_mask"], cb[k]["out_mask"]) for k in ca)
         assert all(torch.equal(v, sb.state_dict()[k]) for k, v in sa.state_dict().items())
+
+
+def test_thresholds_and_masks_live_reference_adversarial_scores():
+    """`get_thresh` / `gen_channel_mask` (pruners/dcfp_pruner.py:43-92) of the LIVE reference against the product's single
+    select call (oracle backend on CPU) on score sets built to hit the rules the golden sweeps only touch by accident:
+    heavily tied (quantised) scores, all-equal and all-zero scores, a threshold sitting on a tie, the min-keep fallback
+    on every layer, layer_keep = 0 (-> 1 channel) and large layer_keep, global_percent at both ends of its range.
+    Both pruners are prepared once (the 10 s trace) and re-used: thresholds and masks are pure functions of
+    (scores, global_percent, layer_keep) afterwards."""
+    ref = ref_compat.load_reference()
+    base = gu.build_model("c1")
+    names = [n for n, m in base.named_modules() if isinstance(m, torch.nn.BatchNorm2d) and n not in base.ignore_prune_layer]
+    sizes = {n: base.get_submodule(n).weight.numel() for n in names}
+    path = "/tmp/_live_adv_score.pth"
+    torch.save({"eic": {n: torch.zeros(c) for n, c in sizes.items()}}, path)
+
+    def prepared(cls):
+        pr = cls(global_percent=0.5, layer_keep=0.02, score_file=path)
+        m = copy.deepcopy(base)
+        pr.end_nodes = getattr(m, "end_nodes", [])
+        pr.prepare_from_supernet(m)
+        pr.except_start_keys = pr.except_start_keys + m.ignore_prune_layer + ["conv_deepsup"]
+        pr.get_except_layers(m)
+        return pr
+
+    from dcfp_b200.pruners.dcfp_pruner import DCFPPruner
+    pr, pm = prepared(ref.dp.DCFPPruner), prepared(DCFPPruner)
+    assert list(pr.norm_conv_links.items()) == list(pm.norm_conv_links.items()) and pr.except_layers == pm.except_layers
+    rng = np.random.RandomState(5)
+
+    def scores(kind):
+        out = {}
+        for n, c in sizes.items():
+            if kind == "quantised":      # 8 distinct values: every threshold sits inside a run of ties
+                s = rng.randint(0, 8, c).astype(np.float32) * 0.125
+            elif kind == "all_equal":
+                s = np.full(c, 0.25, np.float32)
+            elif kind == "all_zero":
+                s = np.zeros(c, np.float32)
+            elif kind == "one_hot":      # a single non-zero channel per layer: masks come from the min-keep fallback almost everywhere
+                s = np.zeros(c, np.float32)
+                s[rng.randint(c)] = rng.rand() + 0.5
+            elif kind == "denormal":     # scores around the smallest fp32 normals and below (an EIC that was gated off for 10^4 steps)
+                s = (rng.rand(c) * 4e-38).astype(np.float32)
+                s[rng.rand(c) < 0.5] = 0.0
+            else:                        # "signed": the EIC is never negative, the pruner must not assume so
+                s = rng.standard_normal(c).astype(np.float32)
+            out[n] = torch.from_numpy(s)
+        return out
+
+    cases = [(k, gp, lk) for k in ("quantised", "all_equal", "all_zero", "one_hot", "denormal", "signed")
+             for gp, lk in ((0.0, 0.02), (0.5, 0.0), (0.62, 0.02), (0.9, 0.5), (0.999, 0.02))]
+    tie_breaks = 0
+    with oracle_backend():
+        for kind, gp, lk in cases:
+            eic = scores(kind)
+            for p in (pr, pm):
+                p.eic, p.global_percent, p.layer_keep = eic, gp, lk
+            t_r = [float(t) for t in pr.get_thresh()]
+            t_m = [float(t) for t in pm.get_thresh()]
+            assert np.array_equal(np.float32(t_r).view(np.uint32), np.float32(t_m).view(np.uint32)), (kind, gp, lk, t_r, t_m)
+            pr.gen_channel_mask()
+            pm.gen_channel_mask()
+            for bn, conv in pr.norm_conv_links.items():
+                if conv in pr.except_layers:
+                    continue
+                a, b = pr.name2module[conv].out_mask, pm.name2module[conv].out_mask
+                assert a.shape == b.shape and a.dtype == b.dtype, (kind, gp, lk, bn)
+                if torch.equal(a, b):
+                    continue
+                # The only licensed difference: the min-keep fallback (:82-84) takes `torch.sort(score, descending=True)[:k]`,
+                # an UNSTABLE sort -- among channels whose score equals the k-th largest, which ones it returns is an
+                # implementation detail of torch's CPU sort (n > 16).  The product keeps the lowest indices among them
+                # (= a stable sort).  Same number of channels, same kept scores, differences only inside that tie.
+                tie_breaks += 1
+                sc, fa, fb = eic[bn], a.reshape(-1) == 1, b.reshape(-1) == 1
+                assert int(fa.sum()) == int(fb.sum()) == max(int(sc.numel() * lk), 1), (kind, gp, lk, bn)
+                assert torch.equal(sc[fa].sort().values, sc[fb].sort().values), (kind, gp, lk, bn)
+                cut = sc[fa].min()
+                assert bool((sc[fa != fb] == cut).all()) and int((sc == cut).sum()) > int((sc[fa] == cut).sum()), (kind, gp, lk, bn)
+    assert tie_breaks > 0  # the quantised / all-equal sets do reach the rule
+    with pytest.raises(IndexError):  # global_percent = 1.0 indexes one past the sorted scores: both raise
+        pr.global_percent = 1.0
+        pr.get_thresh()
+    with oracle_backend(), pytest.raises(IndexError):
+        pm.global_percent = 1.0
+        pm.get_thresh()
